@@ -1,0 +1,97 @@
+// Shared device-side definitions for the spectrogram kernels (sm_100a).
+//
+// Path restated: Web Audio AnalyserNode "FFT windowing and smoothing over time" as the
+// reference drives it (src/javascripts/UI/player.js:7-11, src/javascripts/3D/visualizer.js:346-368):
+// time block -> window -> DFT/N -> |X| -> smoothing -> 20 log10 -> byte / colour.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg {
+
+enum : int { kOutU8 = 0, kOutF32Db = 1, kOutRgba8 = 2, kOutF32Mag = 3 };
+
+// Where frames come from.  Frame f (global index) belongs to clip f / frames_per_clip and is
+// frame t = f % frames_per_clip of that clip; it covers samples [start0 + t*hop, +n_fft) of the
+// clip, zero filled outside [0, clip_len)  (AnalyserNode's ring starts zero filled).
+struct FrameGeom {
+  const float* pcm;          // [n_clips][clip_stride]
+  long long clip_len;
+  long long clip_stride;
+  long long frames_per_clip;
+  long long total_frames;
+  long long start0;          // 0 (valid alignment), hop - n_fft (analyser alignment), ...
+  int n_fft;
+  int hop;
+};
+
+// Epilogue constants, all derived on the host in double.
+//   p = |X'|^2 where X' = norm * X/N is what the kernel holds (norm folds 1/N and any constant
+//   factor the butterflies dropped).
+//   dB   = db_scale * log2(p) + db_off              (= 20 log10(|X|/N))
+//   byte = clamp(byte_a * log2(p) + byte_b, 0, 255) (= 255/(max-min) * (dB - min))
+//   mag  = sqrt(p) * mag_scale
+// and, for values that are already linear magnitudes m (after smoothing):
+//   dB = 2*db_scale*log2(m);  byte = clamp(2*byte_a*log2(m) + byte_b0, 0, 255)
+struct Epilogue {
+  float db_scale;   // 10*log10(2)
+  float db_off;     // -20*log10(norm)
+  float byte_a;     // 255/(max-min) * 10*log10(2)
+  float byte_b;     // 255/(max-min) * (db_off - min_db)
+  float byte_b0;    // 255/(max-min) * (-min_db)
+  float mag_scale;  // 1/norm
+  const uint32_t* lut;  // device, 256 entries (RGBA8 output only)
+};
+
+template <int OUT> struct OutElem { using type = float; };
+template <> struct OutElem<kOutU8> { using type = uint8_t; };
+template <> struct OutElem<kOutRgba8> { using type = uint32_t; };
+
+// [SPEC] "if X^[k] is NaN or infinite, set it to 0"
+__device__ __forceinline__ float finite_or_zero(float v) { return (fabsf(v) <= 3.4028235e38f) ? v : 0.f; }
+
+__device__ __forceinline__ unsigned byte_from_scaled(float v) {
+  v = fminf(fmaxf(v, 0.f), 255.f);  // fmaxf(NaN, 0) = 0
+  return (unsigned)v;               // truncation, as static_cast<unsigned char> in Chromium
+}
+
+// from unnormalised power p = re^2 + im^2  (tau == 0 path: no sqrt needed)
+template <int OUT>
+__device__ __forceinline__ typename OutElem<OUT>::type emit_power(float p, const Epilogue& e) {
+  p = finite_or_zero(p);
+  if constexpr (OUT == kOutF32Mag) {
+    return sqrtf(p) * e.mag_scale;
+  } else {
+    const float l = __log2f(p);
+    if constexpr (OUT == kOutF32Db) {
+      return fmaf(e.db_scale, l, e.db_off);
+    } else {
+      const unsigned b = byte_from_scaled(fmaf(e.byte_a, l, e.byte_b));
+      if constexpr (OUT == kOutU8) return (uint8_t)b;
+      else return __ldg(e.lut + b);
+    }
+  }
+}
+
+// from a linear magnitude m (tau > 0 path, after the recurrence)
+template <int OUT>
+__device__ __forceinline__ typename OutElem<OUT>::type emit_mag(float m, const Epilogue& e) {
+  if constexpr (OUT == kOutF32Mag) {
+    return m;
+  } else {
+    const float l = __log2f(m);
+    if constexpr (OUT == kOutF32Db) {
+      return 2.f * e.db_scale * l;
+    } else {
+      const unsigned b = byte_from_scaled(fmaf(2.f * e.byte_a, l, e.byte_b0));
+      if constexpr (OUT == kOutU8) return (uint8_t)b;
+      else return __ldg(e.lut + b);
+    }
+  }
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+}  // namespace sg

@@ -1,0 +1,706 @@
+// libsgcore.so -- host core + C ABI (include/sgcore.h) of the B200 spectrogram engine.
+//
+// Replaces the browser AnalyserNode the reference configures at src/javascripts/UI/player.js:7-11
+// and polls at src/javascripts/3D/visualizer.js:346-368.  No CPU fallback: every compute entry
+// point runs CUDA kernels (kernel_w32.cuh, kernel_smem.cuh, kernel_misc.cuh) or fails.
+#include "../../include/sgcore.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernel_misc.cuh"
+#include "kernel_smem.cuh"
+#include "kernel_w32.cuh"
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define SG_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(_e == cudaErrorMemoryAllocation ? SG_ERR_OOM : SG_ERR_CUDA,              \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+  } while (0)
+
+#define SG_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != SG_OK) return _rc; \
+  } while (0)
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// ------------------------------------------------------------------------------------------
+// plans: device tables for one (n_fft, window)
+// ------------------------------------------------------------------------------------------
+struct PlanKey {
+  int n_fft, window;
+  uint64_t custom_hash;
+  bool operator<(const PlanKey& o) const {
+    if (n_fft != o.n_fft) return n_fft < o.n_fft;
+    if (window != o.window) return window < o.window;
+    return custom_hash < o.custom_hash;
+  }
+};
+
+struct Plan {
+  int n_fft = 0, m = 0;
+  std::vector<int> radix;
+  float* win = nullptr;
+  float2* tw = nullptr;
+  float2* ut = nullptr;
+  int* pos = nullptr;
+  float2* w32_tw2 = nullptr;  // only n_fft == 2048
+  float2* w32_ut = nullptr;
+  void release() {
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut);
+  }
+};
+
+bool factorize(int m, std::vector<int>& radix) {
+  radix.clear();
+  while (m % 4 == 0) { radix.push_back(4); m /= 4; }
+  while (m % 2 == 0) { radix.push_back(2); m /= 2; }
+  while (m % 5 == 0) { radix.push_back(5); m /= 5; }
+  while (m % 3 == 0) { radix.push_back(3); m /= 3; }
+  return m == 1 && radix.size() <= 16;
+}
+
+void window_table(int kind, int n, const float* custom, std::vector<float>& w) {
+  w.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const double x = (double)i / (double)n;
+    double v;
+    switch (kind) {
+      case SG_WINDOW_BLACKMAN: {
+        const double alpha = 0.16, a0 = 0.5 * (1 - alpha), a1 = 0.5, a2 = 0.5 * alpha;
+        v = a0 - a1 * std::cos(2 * kPi * x) + a2 * std::cos(4 * kPi * x);
+        break;
+      }
+      case SG_WINDOW_HANN: v = 0.5 - 0.5 * std::cos(2 * kPi * x); break;
+      case SG_WINDOW_CUSTOM: v = custom[i]; break;
+      default: v = 1.0;
+    }
+    w[i] = (float)v;  // computed in double, cast to float (as Chromium's ApplyWindow)
+  }
+}
+
+uint64_t fnv1a(const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+float2 expi(double turns) {  // exp(-2 pi i turns)
+  return make_float2((float)std::cos(-2 * kPi * turns), (float)std::sin(-2 * kPi * turns));
+}
+
+template <class T>
+int upload(T** dst, const std::vector<T>& src) {
+  SG_CUDA(cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+  SG_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return SG_OK;
+}
+
+int build_plan(const sg_stft_config& cfg, Plan& p) {
+  p.n_fft = cfg.n_fft;
+  p.m = cfg.n_fft / 2;
+  if (!factorize(p.m, p.radix)) return fail(SG_ERR_INDEX_SIZE, "n_fft/2 must factor into 2, 3, 5");
+  const int m = p.m, n = p.n_fft;
+  std::vector<float> win;
+  window_table(cfg.window, n, cfg.custom_window, win);
+  std::vector<float2> tw(m), ut(m / 2 + 1);
+  for (int k = 0; k < m; ++k) tw[k] = expi((double)k / m);
+  for (int k = 0; k <= m / 2; ++k) ut[k] = expi((double)k / n);
+  // digit reversal of the in-place DIF: k = q1 + R1*(q2 + R2*(...)) sits at sum q_i * m/(R1..Ri)
+  std::vector<int> pos(m);
+  for (int k = 0; k < m; ++k) {
+    int rem = k, span = m, at = 0;
+    for (int r : p.radix) { span /= r; at += (rem % r) * span; rem /= r; }
+    pos[k] = at;
+  }
+  SG_TRY(upload(&p.win, win));
+  SG_TRY(upload(&p.tw, tw));
+  SG_TRY(upload(&p.ut, ut));
+  SG_TRY(upload(&p.pos, pos));
+  if (n == sg::kW32N) {
+    std::vector<float2> tw2(31 * 32), ut32(16 * 32);
+    for (int u = 1; u <= 5; ++u) {
+      const int half = 1 << (u - 1);
+      for (int q = 0; q < half; ++q)
+        for (int lane = 0; lane < 32; ++lane)
+          tw2[(half - 1 + q) * 32 + lane] = expi((double)(q * 32 + lane) / (32.0 * 2 * half));
+    }
+    for (int i = 0; i < 16; ++i)
+      for (int lane = 0; lane < 32; ++lane) ut32[i * 32 + lane] = expi((double)(lane + 32 * i) / n);
+    SG_TRY(upload(&p.w32_tw2, tw2));
+    SG_TRY(upload(&p.w32_ut, ut32));
+  }
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// colour LUT (bin/shaders/sonogram-vertex.shader:19-58, sonogram-fragment.shader:24-26)
+// ------------------------------------------------------------------------------------------
+void hsv_to_rgb(double hue, double* rgb) {
+  const double chroma = 1.0, hd = hue / 60.0;
+  const double x = chroma * (1.0 - std::fabs(std::fmod(hd, 2.0) - 1.0));
+  rgb[0] = rgb[1] = rgb[2] = 0.0;
+  if (hd < 1.0) { rgb[0] = chroma; rgb[1] = x; }
+  else if (hd < 2.0) { rgb[0] = x; rgb[1] = chroma; }
+  else if (hd < 3.0) { rgb[1] = chroma; rgb[2] = x; }
+  else if (hd < 4.0) { rgb[1] = x; rgb[2] = chroma; }
+  else if (hd < 5.0) { rgb[0] = x; rgb[2] = chroma; }
+  else if (hd < 6.0) { rgb[0] = chroma; rgb[2] = x; }
+  // hd == 6 (byte 0) matches no branch in the shader: black
+}
+
+void reference_lut(uint32_t* lut) {
+  const double bg = 0.08;  // 3D/visualizer.js:69
+  for (int b = 0; b < 256; ++b) {
+    const double a = b / 255.0;
+    double rgb[3];
+    hsv_to_rgb(360.0 - a * 360.0, rgb);
+    uint32_t px = 0xFF000000u;
+    for (int c = 0; c < 3; ++c) {
+      const double v = std::min(std::max(bg + a * rgb[c], 0.0), 1.0);
+      px |= (uint32_t)std::floor(v * 255.0 + 0.5) << (8 * c);
+    }
+    lut[b] = px;
+  }
+}
+
+int validate_cfg(const sg_stft_config* cfg) {
+  if (!cfg) return fail(SG_ERR_INVALID_ARG, "cfg is null");
+  if (cfg->n_fft < 4 || cfg->n_fft > 32768 || (cfg->n_fft & 1))
+    return fail(SG_ERR_INDEX_SIZE, "n_fft must be even and in [4, 32768]");
+  std::vector<int> r;
+  if (!factorize(cfg->n_fft / 2, r)) return fail(SG_ERR_INDEX_SIZE, "n_fft/2 must factor into 2, 3, 5");
+  if (cfg->hop < 1) return fail(SG_ERR_INDEX_SIZE, "hop must be >= 1");
+  if (cfg->window < SG_WINDOW_BLACKMAN || cfg->window > SG_WINDOW_CUSTOM)
+    return fail(SG_ERR_INVALID_ARG, "unknown window");
+  if (cfg->window == SG_WINDOW_CUSTOM && !cfg->custom_window)
+    return fail(SG_ERR_INVALID_ARG, "custom window pointer is null");
+  if (cfg->output < SG_OUT_U8 || cfg->output > SG_OUT_F32_MAG) return fail(SG_ERR_INVALID_ARG, "unknown output kind");
+  if (cfg->align != SG_ALIGN_VALID && cfg->align != SG_ALIGN_ANALYSER) return fail(SG_ERR_INVALID_ARG, "unknown alignment");
+  if (!(cfg->min_db < cfg->max_db)) return fail(SG_ERR_INDEX_SIZE, "minDecibels must be < maxDecibels");
+  if (!(cfg->smoothing >= 0.f && cfg->smoothing <= 1.f))
+    return fail(SG_ERR_INDEX_SIZE, "smoothingTimeConstant must be in [0, 1]");
+  return SG_OK;
+}
+
+long long frames_for(const sg_stft_config& c, long long clip_len) {
+  if (c.align == SG_ALIGN_VALID) return clip_len < c.n_fft ? 0 : 1 + (clip_len - c.n_fft) / c.hop;
+  return clip_len / c.hop;
+}
+
+size_t elem_bytes(int output) { return output == SG_OUT_U8 ? 1 : 4; }
+
+sg::Epilogue make_epilogue(const sg_stft_config& c, double norm, const uint32_t* lut_dev) {
+  sg::Epilogue e;
+  const double db_scale = 10.0 * std::log10(2.0);
+  const double db_off = -20.0 * std::log10(norm);
+  const double s = 255.0 / ((double)c.max_db - (double)c.min_db);
+  e.db_scale = (float)db_scale;
+  e.db_off = (float)db_off;
+  e.byte_a = (float)(s * db_scale);
+  e.byte_b = (float)(s * (db_off - (double)c.min_db));
+  e.byte_b0 = (float)(s * (-(double)c.min_db));
+  e.mag_scale = (float)(1.0 / norm);
+  e.lut = lut_dev;
+  return e;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return SG_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    SG_CUDA(cudaMalloc(&p, n));
+    cap = n;
+    return SG_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return SG_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    SG_CUDA(cudaHostAlloc(&p, n, cudaHostAllocDefault));
+    cap = n;
+    return SG_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------
+struct sg_engine {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;     // compute
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::map<PlanKey, Plan> plans;
+  uint32_t* lut_ref = nullptr;       // device, reference colour map
+  DevBuf lut_user;                   // device copy of cfg.colormap
+  DevBuf scratch_mag, scratch_state, d_in, d_out;
+  PinBuf pin_in[2], pin_out[2];
+  int64_t launches = 0;
+  int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
+  bool w32_attr[4] = {false, false, false, false};   // per-device function attributes already set
+  size_t smem_attr[4] = {0, 0, 0, 0};
+  const char* last_kernel = "none";
+  std::mutex mu;
+
+  int get_plan(const sg_stft_config& cfg, Plan** out) {
+    PlanKey key{cfg.n_fft, cfg.window,
+                cfg.window == SG_WINDOW_CUSTOM ? fnv1a(cfg.custom_window, sizeof(float) * cfg.n_fft) : 0};
+    auto it = plans.find(key);
+    if (it == plans.end()) {
+      Plan p;
+      int rc = build_plan(cfg, p);
+      if (rc != SG_OK) { p.release(); return rc; }
+      it = plans.emplace(key, p).first;
+    }
+    *out = &it->second;
+    return SG_OK;
+  }
+
+  int lut_for(const sg_stft_config& cfg, cudaStream_t st, const uint32_t** out) {
+    if (!cfg.colormap) { *out = lut_ref; return SG_OK; }
+    SG_TRY(lut_user.reserve(256 * sizeof(uint32_t)));
+    SG_CUDA(cudaMemcpyAsync(lut_user.p, cfg.colormap, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    *out = (const uint32_t*)lut_user.p;
+    return SG_OK;
+  }
+};
+
+namespace {
+
+template <int OUT>
+int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg_stft_config& cfg,
+                    const uint32_t* lut, void* out, cudaStream_t st) {
+  using T = typename sg::OutElem<OUT>::type;
+  if (g.total_frames <= 0) return SG_OK;
+  if (pl.n_fft == sg::kW32N && e->kernel_variant == 0) {
+    bool* attr_set = e->w32_attr;
+    if (!attr_set[OUT]) {
+      SG_CUDA(cudaFuncSetAttribute(sg::stft_w32_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   sg::kW32SmemBytes));
+      attr_set[OUT] = true;
+    }
+    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+    const long long ctas_needed = (g.total_frames + sg::kW32Warps - 1) / sg::kW32Warps;
+    const int grid = (int)std::min<long long>(ctas_needed, 2LL * e->sm_count);
+    sg::stft_w32_kernel<OUT><<<grid, sg::kW32Warps * 32, sg::kW32SmemBytes, st>>>(g, wp, ep, (T*)out);
+    e->last_kernel = "warp32x32";
+  } else {
+    sg::SmemPlan sp;
+    sp.win = pl.win; sp.tw = pl.tw; sp.ut = pl.ut; sp.pos = pl.pos; sp.m = pl.m;
+    sp.nstage = (int)pl.radix.size();
+    for (int i = 0; i < sp.nstage; ++i) sp.radix[i] = pl.radix[i];
+    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+    const size_t smem = sizeof(float2) * pl.m;
+    size_t* attr_smem = e->smem_attr;
+    if (smem > 48 * 1024 && attr_smem[OUT] < smem) {
+      SG_CUDA(cudaFuncSetAttribute(sg::stft_smem_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      attr_smem[OUT] = smem;
+    }
+    int threads = std::min(1024, std::max(32, ((pl.m / 4 + 31) / 32) * 32));
+    const int per_sm = std::max(1, std::min<int>(2048 / threads, (int)((200 * 1024) / std::max<size_t>(smem, 1024))));
+    const int grid = (int)std::min<long long>(g.total_frames, (long long)e->sm_count * per_sm);
+    sg::stft_smem_kernel<OUT><<<grid, threads, smem, st>>>(g, sp, ep, (T*)out);
+    e->last_kernel = "smem";
+  }
+  e->launches++;
+  SG_CUDA(cudaGetLastError());
+  return SG_OK;
+}
+
+int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg_stft_config& cfg, int out_kind,
+                  const uint32_t* lut, void* out, cudaStream_t st) {
+  switch (out_kind) {
+    case SG_OUT_U8: return launch_frames_t<sg::kOutU8>(e, pl, g, cfg, lut, out, st);
+    case SG_OUT_F32_DB: return launch_frames_t<sg::kOutF32Db>(e, pl, g, cfg, lut, out, st);
+    case SG_OUT_RGBA8: return launch_frames_t<sg::kOutRgba8>(e, pl, g, cfg, lut, out, st);
+    default: return launch_frames_t<sg::kOutF32Mag>(e, pl, g, cfg, lut, out, st);
+  }
+}
+
+template <int OUT>
+int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, long long n_clips, long long frames,
+                    int bins, double tau, const sg::Epilogue& ep, cudaStream_t st) {
+  using T = typename sg::OutElem<OUT>::type;
+  const long long n = n_clips * bins;
+  if (n <= 0 || frames <= 0) return SG_OK;
+  sg::smooth_emit_kernel<OUT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mags, (T*)out, state, n_clips, frames,
+                                                                          bins, tau, ep);
+  e->launches++;
+  SG_CUDA(cudaGetLastError());
+  return SG_OK;
+}
+
+int launch_smooth(sg_engine* e, int out_kind, const float* mags, void* out, float* state, long long n_clips,
+                  long long frames, int bins, double tau, const sg::Epilogue& ep, cudaStream_t st) {
+  switch (out_kind) {
+    case SG_OUT_U8: return launch_smooth_t<sg::kOutU8>(e, mags, out, state, n_clips, frames, bins, tau, ep, st);
+    case SG_OUT_F32_DB: return launch_smooth_t<sg::kOutF32Db>(e, mags, out, state, n_clips, frames, bins, tau, ep, st);
+    case SG_OUT_RGBA8: return launch_smooth_t<sg::kOutRgba8>(e, mags, out, state, n_clips, frames, bins, tau, ep, st);
+    default: return launch_smooth_t<sg::kOutF32Mag>(e, mags, out, state, n_clips, frames, bins, tau, ep, st);
+  }
+}
+
+// One launch group over `n_clips` clips x frames [t0, t0+nframes) of each clip.
+// tau == 0: a single fused kernel.  tau > 0: frame kernel -> linear magnitudes (scratch) ->
+// recurrence + dB/byte kernel, chained through `state` ([n_clips][bins]).
+int run_range(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const float* pcm_dev, long long n_clips,
+              long long clip_len, long long clip_stride, long long t0, long long nframes, long long frames_total,
+              void* out_dev, float* state, const uint32_t* lut, cudaStream_t st) {
+  const int bins = cfg.n_fft / 2;
+  const long long start0 = (cfg.align == SG_ALIGN_VALID ? 0 : (long long)cfg.hop - cfg.n_fft) + t0 * cfg.hop;
+  const size_t eb = elem_bytes(cfg.output);
+  if (cfg.smoothing == 0.f) {
+    if (n_clips == 1 || nframes == frames_total) {
+      sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
+      char* o = (char*)out_dev + (size_t)t0 * bins * eb;
+      return launch_frames(e, pl, g, cfg, cfg.output, lut, o, st);
+    }
+    for (long long c = 0; c < n_clips; ++c) {  // partial frame range of several clips: per clip
+      sg::FrameGeom g{pcm_dev + c * clip_stride, clip_len, clip_stride, nframes, nframes, start0, cfg.n_fft, cfg.hop};
+      char* o = (char*)out_dev + ((size_t)c * frames_total + t0) * bins * eb;
+      SG_TRY(launch_frames(e, pl, g, cfg, cfg.output, lut, o, st));
+    }
+    return SG_OK;
+  }
+  // tau > 0: bound the scratch, walk clip groups
+  const size_t per_clip = (size_t)nframes * bins * sizeof(float);
+  const long long group = std::max<long long>(1, std::min<long long>(n_clips, (long long)((1ull << 30) / std::max<size_t>(per_clip, 1))));
+  SG_TRY(e->scratch_mag.reserve((size_t)group * per_clip));
+  const sg::Epilogue ep = make_epilogue(cfg, 2.0 * cfg.n_fft, lut);
+  for (long long c0 = 0; c0 < n_clips; c0 += group) {
+    const long long nc = std::min(group, n_clips - c0);
+    sg::FrameGeom g{pcm_dev + c0 * clip_stride, clip_len, clip_stride, nframes, nc * nframes, start0, cfg.n_fft, cfg.hop};
+    SG_TRY(launch_frames(e, pl, g, cfg, SG_OUT_F32_MAG, lut, e->scratch_mag.p, st));
+    if (nframes == frames_total) {
+      char* o = (char*)out_dev + (size_t)c0 * frames_total * bins * eb;
+      SG_TRY(launch_smooth(e, cfg.output, (const float*)e->scratch_mag.p, o, state + c0 * bins, nc, nframes, bins,
+                           cfg.smoothing, ep, st));
+    } else {
+      for (long long c = 0; c < nc; ++c) {
+        char* o = (char*)out_dev + ((size_t)(c0 + c) * frames_total + t0) * bins * eb;
+        SG_TRY(launch_smooth(e, cfg.output, (const float*)e->scratch_mag.p + (size_t)c * nframes * bins, o,
+                             state + (c0 + c) * bins, 1, nframes, bins, cfg.smoothing, ep, st));
+      }
+    }
+  }
+  return SG_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI: library
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sg_last_error(void) { return g_err.c_str(); }
+int sg_version(void) { return SG_VERSION_MAJOR * 100 + SG_VERSION_MINOR; }
+
+int sg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int sg_stft_config_default(sg_stft_config* cfg) {
+  if (!cfg) return fail(SG_ERR_INVALID_ARG, "cfg is null");
+  cfg->n_fft = 2048; cfg->hop = 512; cfg->window = SG_WINDOW_BLACKMAN; cfg->output = SG_OUT_U8;
+  cfg->align = SG_ALIGN_VALID; cfg->min_db = -100.f; cfg->max_db = -30.f; cfg->smoothing = 0.f;
+  cfg->custom_window = nullptr; cfg->colormap = nullptr;
+  return SG_OK;
+}
+
+int sg_colormap_reference(uint32_t lut[256]) {
+  if (!lut) return fail(SG_ERR_INVALID_ARG, "lut is null");
+  reference_lut(lut);
+  return SG_OK;
+}
+
+int sg_stft_num_bins(const sg_stft_config* cfg) { return cfg ? cfg->n_fft / 2 : SG_ERR_INVALID_ARG; }
+int64_t sg_stft_num_frames(const sg_stft_config* cfg, int64_t clip_len) {
+  if (validate_cfg(cfg) != SG_OK) return -1;
+  if (clip_len < 0) return -1;
+  return frames_for(*cfg, clip_len);
+}
+int sg_stft_elem_bytes(const sg_stft_config* cfg) { return cfg ? (int)elem_bytes(cfg->output) : SG_ERR_INVALID_ARG; }
+
+// ------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------
+int sg_engine_create(int device, sg_engine** out) {
+  if (!out) return fail(SG_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SG_ERR_NO_DEVICE, "no CUDA device visible (this engine has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(SG_ERR_INVALID_ARG, "device index out of range");
+  SG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SG_ERR_NO_DEVICE, "device is not Blackwell (sm_100a kernels only)");
+  sg_engine* e = new sg_engine();
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  SG_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  SG_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+  SG_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  uint32_t lut[256];
+  reference_lut(lut);
+  SG_CUDA(cudaMalloc((void**)&e->lut_ref, sizeof(lut)));
+  SG_CUDA(cudaMemcpy(e->lut_ref, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  *out = e;
+  return SG_OK;
+}
+
+int sg_engine_destroy(sg_engine* e) {
+  if (!e) return SG_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->plans) kv.second.release();
+  cudaFree(e->lut_ref);
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->d_in.release(); e->d_out.release();
+  for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
+  cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
+  delete e;
+  return SG_OK;
+}
+
+int sg_engine_device(const sg_engine* e) { return e ? e->device : SG_ERR_INVALID_ARG; }
+int64_t sg_engine_launch_count(const sg_engine* e) { return e ? e->launches : 0; }
+const char* sg_engine_last_kernel(const sg_engine* e) { return e ? e->last_kernel : "none"; }
+int sg_engine_set_kernel_variant(sg_engine* e, int variant) {
+  if (!e || variant < 0 || variant > 1) return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto) or 1 (generic)");
+  e->kernel_variant = variant;
+  return SG_OK;
+}
+int sg_engine_synchronize(sg_engine* e) {
+  if (!e) return fail(SG_ERR_INVALID_ARG, "engine is null");
+  SG_CUDA(cudaSetDevice(e->device));
+  SG_CUDA(cudaStreamSynchronize(e->stream));
+  return SG_OK;
+}
+
+int sg_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(SG_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  SG_CUDA(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+  return SG_OK;
+}
+int sg_host_free(void* p) {
+  if (p) SG_CUDA(cudaFreeHost(p));
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched path
+// ------------------------------------------------------------------------------------------
+int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                         const sg_stft_config* cfg, void* out_dev, void* cuda_stream) {
+  if (!e) return fail(SG_ERR_INVALID_ARG, "engine is null");
+  SG_TRY(validate_cfg(cfg));
+  if (n_clips < 0 || clip_len < 0 || clip_stride < clip_len) return fail(SG_ERR_INVALID_ARG, "bad clip geometry");
+  if (n_clips == 0) return SG_OK;
+  if (!pcm_dev || !out_dev) return fail(SG_ERR_INVALID_ARG, "null device buffer");
+  if (((uintptr_t)pcm_dev & 15) || ((uintptr_t)out_dev & 15)) return fail(SG_ERR_INVALID_ARG, "device buffers must be 16-byte aligned");
+  std::lock_guard<std::mutex> lock(e->mu);
+  SG_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  Plan* pl;
+  SG_TRY(e->get_plan(*cfg, &pl));
+  const uint32_t* lut;
+  SG_TRY(e->lut_for(*cfg, st, &lut));
+  const long long frames = frames_for(*cfg, clip_len);
+  if (frames == 0) return SG_OK;
+  float* state = nullptr;
+  if (cfg->smoothing != 0.f) {
+    const size_t sb = (size_t)n_clips * (cfg->n_fft / 2) * sizeof(float);
+    SG_TRY(e->scratch_state.reserve(sb));
+    SG_CUDA(cudaMemsetAsync(e->scratch_state.p, 0, sb, st));
+    state = (float*)e->scratch_state.p;
+  }
+  return run_range(e, *pl, *cfg, pcm_dev, n_clips, clip_len, clip_stride, 0, frames, frames, out_dev, state, lut, st);
+}
+
+// Host buffers.  Work is cut into chunks (groups of whole clips, or frame ranges of one long clip);
+// chunk i+1's host->device copy and chunk i-1's device->host copy overlap chunk i's kernels on three
+// streams.  Pageable host memory is staged through the engine's pinned bounce buffers.
+int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,
+                  void* out) {
+  if (!e) return fail(SG_ERR_INVALID_ARG, "engine is null");
+  SG_TRY(validate_cfg(cfg));
+  if (n_clips < 0 || clip_len < 0) return fail(SG_ERR_INVALID_ARG, "bad clip geometry");
+  if (n_clips == 0) return SG_OK;
+  if (!pcm || !out) return fail(SG_ERR_INVALID_ARG, "null host buffer");
+  std::lock_guard<std::mutex> lock(e->mu);
+  SG_CUDA(cudaSetDevice(e->device));
+  Plan* pl;
+  SG_TRY(e->get_plan(*cfg, &pl));
+  const uint32_t* lut;
+  SG_TRY(e->lut_for(*cfg, e->stream, &lut));
+  const long long frames = frames_for(*cfg, clip_len);
+  if (frames == 0) return SG_OK;
+  const int bins = cfg->n_fft / 2;
+  const size_t eb = elem_bytes(cfg->output);
+  const size_t in_bytes = (size_t)n_clips * clip_len * sizeof(float);
+  const size_t out_bytes = (size_t)n_clips * frames * bins * eb;
+  // device-resident copies of the whole problem (clip_stride padded to 4 floats for 16-byte rows)
+  const long long stride = (clip_len + 3) & ~3LL;
+  SG_TRY(e->d_in.reserve((size_t)n_clips * stride * sizeof(float)));
+  SG_TRY(e->d_out.reserve(out_bytes));
+  float* d_in = (float*)e->d_in.p;
+  char* d_out = (char*)e->d_out.p;
+  float* state = nullptr;
+  if (cfg->smoothing != 0.f) {
+    const size_t sb = (size_t)n_clips * bins * sizeof(float);
+    SG_TRY(e->scratch_state.reserve(sb));
+    SG_CUDA(cudaMemsetAsync(e->scratch_state.p, 0, sb, e->stream));
+    state = (float*)e->scratch_state.p;
+  }
+  const bool in_pinned = is_pinned(pcm), out_pinned = is_pinned(out);
+  const size_t kChunk = 32u << 20;  // target bytes per chunk (input side)
+  struct Chunk { long long c0, nc, t0, nt; };
+  std::vector<Chunk> chunks;
+  const size_t clip_bytes = (size_t)clip_len * sizeof(float);
+  if (clip_bytes <= kChunk) {
+    const long long per = std::max<long long>(1, (long long)(kChunk / std::max<size_t>(clip_bytes, 1)));
+    for (long long c = 0; c < n_clips; c += per) chunks.push_back({c, std::min(per, n_clips - c), 0, frames});
+  } else {
+    const long long per = std::max<long long>(1, (long long)(kChunk / ((size_t)cfg->hop * sizeof(float))));
+    for (long long c = 0; c < n_clips; ++c)
+      for (long long t = 0; t < frames; t += per) chunks.push_back({c, 1, t, std::min(per, frames - t)});
+  }
+  const long long start_base = cfg->align == SG_ALIGN_VALID ? 0 : (long long)cfg->hop - cfg->n_fft;
+  std::vector<cudaEvent_t> ev_in(chunks.size()), ev_k(chunks.size());
+  cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};
+  struct Pending { int slot; char* dst; size_t bytes; bool live; } pend[2] = {{0, nullptr, 0, false}, {1, nullptr, 0, false}};
+  int rc = SG_OK;
+  auto drain_out = [&](int slot) -> int {  // copy a finished pinned output bounce to the caller
+    if (!pend[slot].live) return SG_OK;
+    SG_CUDA(cudaEventSynchronize(ev_pin_out[slot]));
+    std::memcpy(pend[slot].dst, e->pin_out[slot].p, pend[slot].bytes);
+    pend[slot].live = false;
+    return SG_OK;
+  };
+  for (auto& ev : ev_in) ev = nullptr;
+  for (auto& ev : ev_k) ev = nullptr;
+  auto body = [&]() -> int {
+    for (int i = 0; i < 2; ++i) {
+      SG_CUDA(cudaEventCreateWithFlags(&ev_pin_in[i], cudaEventDisableTiming));
+      SG_CUDA(cudaEventCreateWithFlags(&ev_pin_out[i], cudaEventDisableTiming));
+    }
+    long long uploaded_to = 0;  // per-clip sample watermark for frame-range chunks
+    long long uploaded_clip = -1;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      const Chunk& ch = chunks[i];
+      const int slot = (int)(i & 1);
+      SG_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      SG_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+      // ---- host -> device
+      long long s_lo, s_hi;  // sample range of each clip in this chunk
+      if (ch.nt == frames) { s_lo = 0; s_hi = clip_len; }
+      else {
+        if (uploaded_clip != ch.c0) { uploaded_clip = ch.c0; uploaded_to = 0; }
+        s_lo = uploaded_to;
+        s_hi = std::min<long long>(clip_len, std::max<long long>(s_lo, start_base + (ch.t0 + ch.nt - 1) * cfg->hop + cfg->n_fft));
+        uploaded_to = s_hi;
+      }
+      const size_t row = (size_t)(s_hi - s_lo) * sizeof(float);
+      if (row > 0) {
+        const float* src = pcm + ch.c0 * clip_len + s_lo;
+        if (!in_pinned) {
+          SG_TRY(e->pin_in[slot].reserve(row * ch.nc));
+          SG_CUDA(cudaEventSynchronize(ev_pin_in[slot]));   // previous use of this bounce has been copied
+          for (long long c = 0; c < ch.nc; ++c)
+            std::memcpy((char*)e->pin_in[slot].p + c * row, src + c * clip_len, row);
+          SG_CUDA(cudaMemcpy2DAsync(d_in + ch.c0 * stride + s_lo, stride * sizeof(float), e->pin_in[slot].p, row, row,
+                                    ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
+          SG_CUDA(cudaEventRecord(ev_pin_in[slot], e->s_h2d));
+        } else {
+          SG_CUDA(cudaMemcpy2DAsync(d_in + ch.c0 * stride + s_lo, stride * sizeof(float), src, clip_bytes, row, ch.nc,
+                                    cudaMemcpyHostToDevice, e->s_h2d));
+        }
+      }
+      SG_CUDA(cudaEventRecord(ev_in[i], e->s_h2d));
+      // ---- kernels
+      SG_CUDA(cudaStreamWaitEvent(e->stream, ev_in[i], 0));
+      SG_TRY(run_range(e, *pl, *cfg, d_in + ch.c0 * stride, ch.nc, clip_len, stride, ch.t0, ch.nt, frames,
+                       d_out + (size_t)ch.c0 * frames * bins * eb, state ? state + ch.c0 * bins : nullptr, lut, e->stream));
+      SG_CUDA(cudaEventRecord(ev_k[i], e->stream));
+      // ---- device -> host
+      SG_CUDA(cudaStreamWaitEvent(e->s_d2h, ev_k[i], 0));
+      const size_t off = ((size_t)ch.c0 * frames + ch.t0) * bins * eb;
+      const size_t nbytes = (ch.nt == frames ? (size_t)ch.nc * frames : (size_t)ch.nt) * bins * eb;
+      if (!out_pinned) {
+        SG_TRY(drain_out(slot));
+        SG_TRY(e->pin_out[slot].reserve(nbytes));
+        SG_CUDA(cudaMemcpyAsync(e->pin_out[slot].p, d_out + off, nbytes, cudaMemcpyDeviceToHost, e->s_d2h));
+        SG_CUDA(cudaEventRecord(ev_pin_out[slot], e->s_d2h));
+        pend[slot] = {slot, (char*)out + off, nbytes, true};
+      } else {
+        SG_CUDA(cudaMemcpyAsync((char*)out + off, d_out + off, nbytes, cudaMemcpyDeviceToHost, e->s_d2h));
+      }
+    }
+    SG_TRY(drain_out(0));
+    SG_TRY(drain_out(1));
+    SG_CUDA(cudaStreamSynchronize(e->s_d2h));
+    SG_CUDA(cudaStreamSynchronize(e->stream));
+    return SG_OK;
+  };
+  rc = body();
+  if (rc != SG_OK) cudaDeviceSynchronize();
+  for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
+  for (auto ev : ev_k) if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) { if (ev_pin_in[i]) cudaEventDestroy(ev_pin_in[i]); if (ev_pin_out[i]) cudaEventDestroy(ev_pin_out[i]); }
+  (void)in_bytes;
+  return rc;
+}
+
+}  // extern "C"
+
+#include "sg_objects.inl"

@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (through the C ABI, via the Python host layer) against the oracle.
+
+Every test here needs a B200: run with ``-m gpu``.  The float64 oracle is the truth; tolerances are
+tests/_tol.py (1e-4 relative magnitude + float32 floor, 1e-3 dB near the peak, +-1 LSB bytes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import spectrogram_b200 as sg
+from oracle import analyser_oracle as O
+from _tol import assert_bytes_close, assert_db_close, assert_mag_close
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+WIN = {O.WINDOW_BLACKMAN: "blackman", O.WINDOW_HANN: "hann", O.WINDOW_RECT: "rect"}
+OUT = {O.OUT_U8: "u8", O.OUT_F32_DB: "db", O.OUT_RGBA8: "rgba", O.OUT_F32_MAG: "mag"}
+ALIGN = {O.ALIGN_VALID: "valid", O.ALIGN_ANALYSER: "analyser"}
+
+
+def opts_of(cfg: O.Config) -> sg.Options:
+    return sg.Options(fftSize=cfg.n_fft, hop=cfg.hop, window=WIN[cfg.window], output=OUT[cfg.output],
+                      align=ALIGN[cfg.align], minDecibels=cfg.min_db, maxDecibels=cfg.max_db,
+                      smoothingTimeConstant=cfg.smoothing)
+
+
+def check_all_outputs(engine, x, cfg: O.Config):
+    """Runs the four output kinds and compares each with the float64 oracle."""
+    base = dict(cfg.__dict__)
+    ref_mag = O.spectrogram(x, O.Config(**{**base, "output": O.OUT_F32_MAG}))
+    got = engine.spectrogram(x, opts_of(O.Config(**{**base, "output": O.OUT_F32_MAG})))
+    assert got.shape == ref_mag.shape and got.dtype == np.float32
+    assert_mag_close(got, ref_mag)
+    got = engine.spectrogram(x, opts_of(O.Config(**{**base, "output": O.OUT_F32_DB})))
+    assert_db_close(got, ref_mag)
+    ref_u8 = O.finish(ref_mag, O.Config(**{**base, "output": O.OUT_U8}))
+    got_u8 = engine.spectrogram(x, opts_of(O.Config(**{**base, "output": O.OUT_U8})))
+    assert got_u8.dtype == np.uint8
+    assert_bytes_close(got_u8, ref_u8)
+    got_rgba = engine.spectrogram(x, opts_of(O.Config(**{**base, "output": O.OUT_RGBA8})))
+    assert got_rgba.shape == ref_u8.shape + (4,)
+    assert np.array_equal(got_rgba, O.colormap_lut()[got_u8])   # LUT applied to the engine's own bytes: exact
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def golden_cases():
+    with open(os.path.join(GOLDEN, "index.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+@pytest.mark.parametrize("variant", [0, 1], ids=["auto", "generic"])
+def test_golden(engine, case, variant):
+    data = np.load(os.path.join(GOLDEN, case["file"]))
+    cfg = O.Config(n_fft=case["n_fft"], hop=case["hop"], window=case["window"], output=case["output"],
+                   align=case["align"], smoothing=case["tau"])
+    engine.set_kernel_variant(variant)
+    try:
+        got = engine.spectrogram(data["pcm"], opts_of(cfg))
+    finally:
+        engine.set_kernel_variant(0)
+    ref = data["out"]
+    assert got.shape == ref.shape
+    if cfg.output == O.OUT_U8:
+        assert_bytes_close(got, ref)
+    elif cfg.output == O.OUT_RGBA8:
+        inv = {tuple(v): i for i, v in enumerate(map(tuple, O.colormap_lut()))}
+        ref_b = np.array([inv[tuple(p)] for p in ref.reshape(-1, 4)]).reshape(ref.shape[:-1])
+        got_b = np.array([inv[tuple(p)] for p in got.reshape(-1, 4)]).reshape(got.shape[:-1])
+        assert_bytes_close(got_b, ref_b)
+    else:
+        ref_mag = O.spectrogram(data["pcm"], O.Config(**{**cfg.__dict__, "output": O.OUT_F32_MAG}))
+        if cfg.output == O.OUT_F32_MAG:
+            assert_mag_close(got, ref_mag)
+        else:
+            assert_db_close(got, ref_mag)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs
+def test_config1_chirp_full(engine):
+    """10 s mono 44.1 kHz chirp, n_fft 2048, hop 512: Blackman (parity) and Hann (as named)."""
+    x = O.chirp(441000, 44100.0, 20.0, 20000.0, 0.5)
+    for window in (O.WINDOW_BLACKMAN, O.WINDOW_HANN):
+        for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
+            cfg = O.Config(window=window, align=align)
+            check_all_outputs(engine, x, cfg)
+            assert engine.last_kernel == "warp32x32"
+    assert engine.spectrogram(x, sg.Options()).shape == (858, 1024)
+    assert engine.spectrogram(x, sg.Options(align="analyser")).shape == (861, 1024)
+
+
+def test_config1_both_kernels_agree(engine):
+    x = O.chirp(100000, 44100.0, 20.0, 20000.0, 0.5)
+    a = engine.spectrogram(x, sg.Options(output="mag"))
+    engine.set_kernel_variant(1)
+    try:
+        b = engine.spectrogram(x, sg.Options(output="mag"))
+        assert engine.last_kernel == "smem"
+    finally:
+        engine.set_kernel_variant(0)
+    assert_mag_close(a, b.astype(np.float64))
+
+
+def test_config2_speech_band_noise(engine):
+    x = O.band_noise(16000 * 20, 16000.0, 300.0, 3400.0, 0.1, 1234)
+    check_all_outputs(engine, x, O.Config(n_fft=512, hop=160, window=O.WINDOW_HANN))
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024, 2048, 4096, 8192])
+def test_config3_fft_sweep_with_smoothing(engine, n_fft):
+    rng = np.random.default_rng(1234)
+    n = 48000 * 2
+    x = np.stack([O.chirp(n, 48000.0, 50.0, 20000.0, 0.4) + (0.01 * rng.standard_normal(n)).astype(np.float32)
+                  for _ in range(2)])
+    check_all_outputs(engine, x, O.Config(n_fft=n_fft, hop=n_fft // 4, smoothing=0.8, align=O.ALIGN_ANALYSER))
+
+
+def test_config4_n400_clips(engine):
+    rng = np.random.default_rng(0)
+    x = (0.1 * rng.standard_normal((16, 16000))).astype(np.float32)
+    check_all_outputs(engine, x, O.Config(n_fft=400, hop=160, window=O.WINDOW_HANN))
+    assert engine.spectrogram(x, sg.Options(fftSize=400, hop=160)).shape == (16, 98, 200)
+
+
+def test_config5_streaming_equals_batch(engine):
+    """256 channels, n_fft 1024, hop 128, one render quantum per push; bytes + colour."""
+    rng = np.random.default_rng(5)
+    ch, chunks = 256, 12
+    x = (0.2 * rng.standard_normal((ch, 128 * chunks))).astype(np.float32)
+    opts = sg.Options(fftSize=1024, hop=128, output="u8")
+    bank = sg.StreamBank(ch, opts, max_chunk=256, engine=engine)
+    rows, rgba_rows = [], []
+    i = 0
+    for step in (128, 256, 128, 256, 256, 128, 256, 128):
+        out, rgba = bank.push(x[:, i:i + step], want_rgba=True)
+        rows.append(out)
+        rgba_rows.append(rgba)
+        i += step
+    assert i == x.shape[1] and bank.frames_emitted == chunks
+    got = np.concatenate(rows, axis=1)
+    got_rgba = np.concatenate(rgba_rows, axis=1)
+    batch = engine.spectrogram(x, sg.Options(fftSize=1024, hop=128, align="analyser"))
+    assert np.array_equal(got, batch)            # streaming == batch, bit exact
+    assert np.array_equal(got_rgba, O.colormap_lut()[got])
+    ref = O.spectrogram(x, O.Config(n_fft=1024, hop=128, align=O.ALIGN_ANALYSER))
+    assert_bytes_close(got, ref)
+    bank.reset()
+    out = bank.push(x[:, :128])
+    assert np.array_equal(out, got[:, :1])
+    bank.close()
+
+
+def test_streaming_with_smoothing_carries_state(engine):
+    rng = np.random.default_rng(6)
+    x = (0.2 * rng.standard_normal((8, 128 * 10))).astype(np.float32)
+    opts = sg.Options(fftSize=512, hop=128, output="db", smoothingTimeConstant=0.8)
+    bank = sg.StreamBank(8, opts, max_chunk=128, engine=engine)
+    got = np.concatenate([bank.push(x[:, i:i + 128]) for i in range(0, x.shape[1], 128)], axis=1)
+    bank.close()
+    ref_mag = O.spectrogram(x, O.Config(n_fft=512, hop=128, align=O.ALIGN_ANALYSER, smoothing=0.8, output=O.OUT_F32_MAG))
+    assert_db_close(got, ref_mag)
+
+
+# ----------------------------------------------------------------------------- sizes and edges
+@pytest.mark.parametrize("n_fft", [32, 64, 128, 4096, 16384, 32768, 6, 10, 12, 60, 100, 1000, 1200, 3000])
+def test_every_legal_size(engine, n_fft):
+    rng = np.random.default_rng(n_fft)
+    hop = max(1, n_fft // 3)
+    x = (0.3 * rng.standard_normal((2, n_fft + 5 * hop + 3))).astype(np.float32)
+    check_all_outputs(engine, x, O.Config(n_fft=n_fft, hop=hop))
+
+
+@pytest.mark.parametrize("hop", [1, 3, 511, 513, 2048, 5000])
+def test_ragged_hops_n2048(engine, hop):
+    """odd hops give 4-byte-aligned frames (the 8-byte fast loads do not apply), hop > n_fft skips samples"""
+    rng = np.random.default_rng(hop)
+    x = (0.3 * rng.standard_normal((3, 2048 + 9 * hop + 1))).astype(np.float32)
+    for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
+        check_all_outputs(engine, x, O.Config(hop=hop, align=align))
+
+
+def test_empty_and_short_inputs(engine):
+    assert engine.spectrogram(np.zeros((3, 100), np.float32), sg.Options()).shape == (3, 0, 1024)
+    assert engine.spectrogram(np.zeros((0, 4096), np.float32), sg.Options()).shape == (0, 5, 1024)
+    out = engine.spectrogram(np.zeros((2, 700), np.float32), sg.Options(align="analyser"))
+    assert out.shape == (2, 1, 1024) and out.max() == 0
+    out = engine.spectrogram(np.ones(2048, np.float32), sg.Options())
+    assert out.shape == (1, 1024)
+
+
+def test_silence_full_scale_and_non_finite(engine):
+    x = np.zeros((1, 4096), np.float32)
+    assert engine.spectrogram(x, sg.Options()).max() == 0
+    db = engine.spectrogram(x, sg.Options(output="db"))
+    assert np.all(np.isneginf(db))
+    loud = np.ones((1, 4096), np.float32) * 30.0
+    assert engine.spectrogram(loud, sg.Options())[0, 0, 0] == 255
+    bad = (0.1 * np.random.default_rng(0).standard_normal((1, 4096))).astype(np.float32)
+    bad[0, 1000] = np.nan
+    out = engine.spectrogram(bad, sg.Options(output="mag"))
+    ref = O.spectrogram(bad, O.Config(output=O.OUT_F32_MAG))
+    assert np.all(np.isfinite(out)) and np.array_equal(out == 0, ref == 0)   # [SPEC] non-finite -> 0
+    assert engine.spectrogram(bad, sg.Options()).max() <= 255
+
+
+def test_db_range_and_custom_window_and_colormap(engine):
+    rng = np.random.default_rng(11)
+    x = (0.05 * rng.standard_normal((2, 8192))).astype(np.float32)
+    cfg = O.Config(min_db=-80.0, max_db=-10.0)
+    check_all_outputs(engine, x, cfg)
+    w = np.kaiser(2048, 8.0)
+    got = engine.spectrogram(x, sg.Options(window=w.astype(np.float32), output="mag"))
+    ref = O.spectrogram(x, O.Config(window=O.WINDOW_CUSTOM, custom_window=w.astype(np.float32), output=O.OUT_F32_MAG))
+    assert_mag_close(got, ref)
+    lut = (np.arange(256, dtype=np.uint32) * 0x01010101)
+    got = engine.spectrogram(x, sg.Options(output="rgba", colormap=lut))
+    by = engine.spectrogram(x, sg.Options())
+    assert np.array_equal(got[..., 0], by) and np.array_equal(got[..., 3], by)
+
+
+def test_invalid_options_raise_like_web_audio(engine):
+    x = np.zeros(8192, np.float32)
+    for kw in (dict(fftSize=2047), dict(fftSize=14), dict(hop=0), dict(minDecibels=-30, maxDecibels=-30),
+               dict(smoothingTimeConstant=1.01)):
+        with pytest.raises(sg.IndexSizeError):
+            engine.spectrogram(x, sg.Options(**kw))
+    with pytest.raises(TypeError):
+        engine.spectrogram(np.zeros((2, 2, 2), np.float32), sg.Options())
+
+
+# ----------------------------------------------------------------------------- AnalyserNode object
+def test_analyser_node_defaults_and_validation(engine):
+    an = sg.AnalyserNode(engine)
+    assert (an.fftSize, an.frequencyBinCount, an.minDecibels, an.maxDecibels, an.smoothingTimeConstant) == \
+        (2048, 1024, -100.0, -30.0, 0.8)
+    for bad in (0, 31, 48, 65536, 2048.5):
+        with pytest.raises(sg.IndexSizeError):
+            an.fftSize = bad
+    with pytest.raises(sg.IndexSizeError):
+        an.minDecibels = -30
+    with pytest.raises(sg.IndexSizeError):
+        an.maxDecibels = -100
+    with pytest.raises(sg.IndexSizeError):
+        an.smoothingTimeConstant = 1.5
+    with pytest.raises(TypeError):
+        an.getByteFrequencyData(np.zeros(1024, np.float32))
+    with pytest.raises(TypeError):
+        an.getFloatFrequencyData([0.0] * 1024)
+    an.fftSize = 1024                      # player.js:10 mobile branch
+    assert an.frequencyBinCount == 512
+    an.close()
+
+
+def test_analyser_node_follows_the_reference_call_pattern(engine):
+    """player.js:7-11 configuration, visualizer.js:346-368 polling, against the oracle object."""
+    rng = np.random.default_rng(2)
+    x = (0.3 * rng.standard_normal(128 * 60)).astype(np.float32)
+    for fft, tau in ((2048, 0.0), (2048, 0.75), (1024, 0.1), (32, 0.8), (32768, 0.5)):
+        an, ref = sg.AnalyserNode(engine), O.AnalyserOracle()
+        an.fftSize = fft
+        ref.fftSize = fft
+        an.smoothingTimeConstant = tau
+        ref.smoothingTimeConstant = tau
+        bins = an.frequencyBinCount
+        by, by_ref = np.zeros(bins, np.uint8), np.zeros(bins, np.uint8)
+        fl, fl_ref = np.zeros(bins, np.float32), np.zeros(bins, np.float64)
+        td, td_ref = np.zeros(fft, np.uint8), np.zeros(fft, np.uint8)
+        tf, tf_ref = np.zeros(fft, np.float32), np.zeros(fft, np.float64)
+        for i in range(0, x.size, 640):   # 5 render quanta between polls
+            an.push(x[i:i + 640])
+            ref.push(x[i:i + 640])
+            an.getByteFrequencyData(by)
+            ref.getByteFrequencyData(by_ref)
+            assert_bytes_close(by, by_ref, max_mismatch_frac=0.05)
+            an.getFloatFrequencyData(fl)   # same quantum: must not advance the smoothing state
+            ref.getFloatFrequencyData(fl_ref)
+            assert_db_close(fl[None], ref._state[None])
+            an.getByteTimeDomainData(td)
+            ref.getByteTimeDomainData(td_ref)
+            assert np.array_equal(td, td_ref)
+            an.getFloatTimeDomainData(tf)
+            ref.getFloatTimeDomainData(tf_ref)
+            assert np.array_equal(tf, tf_ref.astype(np.float32))
+        short = np.full(10, 7, np.uint8)
+        an.getByteFrequencyData(short)          # copies min(len, bins) elements
+        assert np.array_equal(short, by[:10])
+        long_ = np.full(bins + 5, 7, np.uint8)
+        an.getByteFrequencyData(long_)
+        assert np.array_equal(long_[:bins], by) and np.all(long_[bins:] == 7)   # never resizes, tail untouched
+        an.close()
+
+
+# ----------------------------------------------------------------------------- device pointers, sharding
+def test_device_pointer_entry_and_stream(engine):
+    import torch
+    x = O.chirp(200000, 44100.0, 20.0, 20000.0, 0.5)
+    ref = engine.spectrogram(x, sg.Options())
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty(ref.shape, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+    before = engine.launch_count
+    engine.spectrogram_device(xd.data_ptr(), 1, x.size, x.size, sg.Options(), out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert engine.launch_count == before + 1
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_shard_invariance_bit_exact(engine):
+    """1-GPU result == concatenation of per-shard results; also the threaded multi-device host path."""
+    rng = np.random.default_rng(4)
+    x = (0.2 * rng.standard_normal((13, 20000))).astype(np.float32)
+    whole = engine.spectrogram(x, sg.Options())
+    parts = [engine.spectrogram(x[lo:hi], sg.Options()) for lo, hi in sg.shard_bounds(13, 4)]
+    assert np.array_equal(np.concatenate(parts), whole)
+    n_dev = sg.device_count()
+    devs = list(range(n_dev)) if n_dev > 1 else [0, 0, 0]
+    assert np.array_equal(sg.spectrogram(x, devices=devs), whole)
+
+
+def test_pinned_and_pageable_host_buffers_agree(engine):
+    rng = np.random.default_rng(12)
+    x = (0.2 * rng.standard_normal((40, 300000))).astype(np.float32)   # > one 32 MB chunk: exercises the pipeline
+    a = engine.spectrogram(x, sg.Options())
+    pin_in = sg.PinnedArray(x.shape, np.float32)
+    pin_in.array[...] = x
+    pin_out = sg.PinnedArray(a.shape, np.uint8)
+    engine.spectrogram(pin_in.array, sg.Options(), out=pin_out.array)
+    assert np.array_equal(pin_out.array, a)
+    ref = O.spectrogram(x[:2], O.Config())
+    assert_bytes_close(a[:2], ref)
+    pin_in.free()
+    pin_out.free()
+
+
+def test_long_single_clip_is_chunked_over_frames(engine):
+    """config 2 shape (one long stream): frame-range chunks, with and without smoothing carry."""
+    rng = np.random.default_rng(13)
+    x = (0.1 * rng.standard_normal(16000 * 900)).astype(np.float32)   # 57.6 MB > chunk size
+    for tau in (0.0, 0.8):
+        got = engine.spectrogram(x, sg.Options(fftSize=512, hop=160, window="hann", output="db", smoothingTimeConstant=tau))
+        sel = np.r_[0:50, 40000:40050, got.shape[0] - 50:got.shape[0]]
+        if tau == 0.0:
+            ref_mag = O.spectrogram(x, O.Config(n_fft=512, hop=160, window=O.WINDOW_HANN, output=O.OUT_F32_MAG))[0]
+            assert_db_close(got[sel], ref_mag[sel])
+        else:
+            # recurrence across chunk borders: compare around the first border with a local oracle run
+            per = (32 << 20) // (160 * 4)
+            lo = per - 200
+            seg = x[lo * 160: (per + 50) * 160 + 512]
+            ref_mag = O.spectrogram(seg, O.Config(n_fft=512, hop=160, window=O.WINDOW_HANN, smoothing=tau, output=O.OUT_F32_MAG))[0]
+            assert_db_close(got[lo + 150: per + 50], ref_mag[150:250])   # 150 frames of warm-up: 0.8^150 ~ 3e-15
+
+
+# ----------------------------------------------------------------------------- size-independent properties at full size
+def test_properties_at_full_size(engine):
+    """BASELINE-sized batch (64 Ki frames at n_fft 2048 / hop 512): linearity, Parseval, determinism."""
+    import torch
+    frames = 65536
+    n = 2048 + (frames - 1) * 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xd = (torch.rand(n, device="cuda", generator=g) - 0.5) * 0.5
+    opts = sg.Options(output="mag", window="rect")
+    mag = torch.empty((frames, 1024), dtype=torch.float32, device="cuda")
+    mag2 = torch.empty_like(mag)
+    st = torch.cuda.current_stream().cuda_stream
+    engine.spectrogram_device(xd.data_ptr(), 1, n, n, opts, mag.data_ptr(), st)
+    x2 = xd * 2.0
+    engine.spectrogram_device(x2.data_ptr(), 1, n, n, opts, mag2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.allclose(mag2, 2.0 * mag, rtol=1e-5, atol=0)                 # linearity of |X| (exact power of two)
+    # Parseval per frame (rect window): sum_k' |X|^2 = sum x^2 / N, Nyquist bin recomputed separately
+    fr = xd.unfold(0, 2048, 512)
+    sign = torch.ones(2048, device="cuda")
+    sign[1::2] = -1
+    nyq = (fr * sign).sum(dim=1) / 2048
+    energy = mag[:, 0] ** 2 + 2 * (mag[:, 1:] ** 2).sum(dim=1) + nyq ** 2
+    want = (fr ** 2).sum(dim=1) / 2048
+    assert torch.allclose(energy, want, rtol=2e-4)
+    by1 = torch.empty((frames, 1024), dtype=torch.uint8, device="cuda")
+    by2 = torch.empty_like(by1)
+    engine.spectrogram_device(xd.data_ptr(), 1, n, n, sg.Options(), by1.data_ptr(), st)
+    engine.spectrogram_device(xd.data_ptr(), 1, n, n, sg.Options(), by2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(by1, by2)                                              # run-to-run identical
+    # byte monotone in amplitude
+    engine.spectrogram_device(x2.data_ptr(), 1, n, n, sg.Options(), by2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert bool((by2 >= by1).all())
+    # spot-check a slice against the oracle
+    sl = xd[: 2048 + 63 * 512].cpu().numpy()
+    ref = O.spectrogram(sl, O.Config())[0]
+    assert_bytes_close(by1[:64].cpu().numpy(), ref)
