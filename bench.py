@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def start(self):
         if self._nv is not None:
@@ -231,7 +231,8 @@ def run_gpu(args) -> None:
 
     x = synth_clips_gpu(torch, plan["n_clips"], plan["lo"], dev)
     out = torch.empty((plan["n_clips"], frames_per_clip, N_FFT // 2), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)   # the kernels and the timing events share this stream
 
     def step():
         eng.spectrogram_device(x.data_ptr(), plan["n_clips"], CLIP_LEN, CLIP_LEN, opts, out.data_ptr(), stream.cuda_stream)

@@ -19,6 +19,7 @@
 #include "kernel_misc.cuh"
 #include "kernel_smem.cuh"
 #include "kernel_w32.cuh"
+#include "kernel_w32x2.cuh"
 
 namespace {
 
@@ -279,6 +280,7 @@ struct sg_engine {
   int64_t launches = 0;
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   bool w32_attr[4] = {false, false, false, false};   // per-device function attributes already set
+  bool x2_attr[4] = {false, false, false, false};
   size_t smem_attr[4] = {0, 0, 0, 0};
   const char* last_kernel = "none";
   std::mutex mu;
@@ -313,7 +315,24 @@ int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const 
                     const uint32_t* lut, void* out, cudaStream_t st) {
   using T = typename sg::OutElem<OUT>::type;
   if (g.total_frames <= 0) return SG_OK;
-  if (pl.n_fft == sg::kW32N && e->kernel_variant == 0) {
+  // The packed kernel's byte path takes lg2 with subnormal powers flushed to zero (|X|/N < 1e-19, below
+  // -380 dB): exact for any minDecibels above that, otherwise the one-frame kernel is used.
+  const bool x2_ok = !(OUT == sg::kOutU8 || OUT == sg::kOutRgba8) || cfg.min_db >= -300.f;
+  if (pl.n_fft == sg::kW32N && e->kernel_variant == 0 && x2_ok) {
+    // packed two-frames-per-warp kernel (FFMA2), one persistent CTA per SM
+    if (!e->x2_attr[OUT]) {
+      SG_CUDA(cudaFuncSetAttribute(sg::stft_w32x2_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   sg::kX2SmemBytes));
+      e->x2_attr[OUT] = true;
+    }
+    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+    const long long pairs = (g.total_frames + 1) / 2;
+    const long long ctas_needed = (pairs + sg::kX2Warps - 1) / sg::kX2Warps;
+    const int grid = (int)std::min<long long>(ctas_needed, e->sm_count);
+    sg::stft_w32x2_kernel<OUT><<<grid, sg::kX2Warps * 32, sg::kX2SmemBytes, st>>>(g, wp, ep, (T*)out);
+    e->last_kernel = "warp32x32x2";
+  } else if (pl.n_fft == sg::kW32N && e->kernel_variant != 1) {
     bool* attr_set = e->w32_attr;
     if (!attr_set[OUT]) {
       SG_CUDA(cudaFuncSetAttribute(sg::stft_w32_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -515,7 +534,8 @@ int sg_engine_device(const sg_engine* e) { return e ? e->device : SG_ERR_INVALID
 int64_t sg_engine_launch_count(const sg_engine* e) { return e ? e->launches : 0; }
 const char* sg_engine_last_kernel(const sg_engine* e) { return e ? e->last_kernel : "none"; }
 int sg_engine_set_kernel_variant(sg_engine* e, int variant) {
-  if (!e || variant < 0 || variant > 1) return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto) or 1 (generic)");
+  if (!e || variant < 0 || variant > 2)
+    return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto), 1 (generic smem) or 2 (one frame per warp)");
   e->kernel_variant = variant;
   return SG_OK;
 }

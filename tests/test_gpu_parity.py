@@ -29,6 +29,7 @@ def opts_of(cfg: O.Config) -> sg.Options:
 def check_all_outputs(engine, x, cfg: O.Config):
     """Runs the four output kinds and compares each with the float64 oracle."""
     base = dict(cfg.__dict__)
+    x = np.atleast_2d(x)
     ref_mag = O.spectrogram(x, O.Config(**{**base, "output": O.OUT_F32_MAG}))
     got = engine.spectrogram(x, opts_of(O.Config(**{**base, "output": O.OUT_F32_MAG})))
     assert got.shape == ref_mag.shape and got.dtype == np.float32
@@ -51,7 +52,7 @@ def golden_cases():
 
 
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
-@pytest.mark.parametrize("variant", [0, 1], ids=["auto", "generic"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["auto", "generic", "w32"])
 def test_golden(engine, case, variant):
     data = np.load(os.path.join(GOLDEN, case["file"]))
     cfg = O.Config(n_fft=case["n_fft"], hop=case["hop"], window=case["window"], output=case["output"],
@@ -86,7 +87,7 @@ def test_config1_chirp_full(engine):
         for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
             cfg = O.Config(window=window, align=align)
             check_all_outputs(engine, x, cfg)
-            assert engine.last_kernel == "warp32x32"
+            assert engine.last_kernel == "warp32x32x2"
     assert engine.spectrogram(x, sg.Options()).shape == (858, 1024)
     assert engine.spectrogram(x, sg.Options(align="analyser")).shape == (861, 1024)
 
@@ -299,7 +300,8 @@ def test_device_pointer_entry_and_stream(engine):
     ref = engine.spectrogram(x, sg.Options())
     xd = torch.from_numpy(x).cuda()
     out = torch.empty(ref.shape, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
     before = engine.launch_count
     engine.spectrogram_device(xd.data_ptr(), 1, x.size, x.size, sg.Options(), out.data_ptr(), st.cuda_stream)
     st.synchronize()
@@ -364,9 +366,11 @@ def test_properties_at_full_size(engine):
     opts = sg.Options(output="mag", window="rect")
     mag = torch.empty((frames, 1024), dtype=torch.float32, device="cuda")
     mag2 = torch.empty_like(mag)
-    st = torch.cuda.current_stream().cuda_stream
-    engine.spectrogram_device(xd.data_ptr(), 1, n, n, opts, mag.data_ptr(), st)
     x2 = xd * 2.0
+    torch.cuda.synchronize()
+    st_obj = torch.cuda.Stream()
+    st = st_obj.cuda_stream
+    engine.spectrogram_device(xd.data_ptr(), 1, n, n, opts, mag.data_ptr(), st)
     engine.spectrogram_device(x2.data_ptr(), 1, n, n, opts, mag2.data_ptr(), st)
     torch.cuda.synchronize()
     assert torch.allclose(mag2, 2.0 * mag, rtol=1e-5, atol=0)                 # linearity of |X| (exact power of two)
