@@ -180,7 +180,9 @@ __device__ __forceinline__ void window_stage1(C2& lo, C2& hi, float2 a0, float2 
   hi.im = P2(fmaf(a1.y, -w1.y, ua), fmaf(b1.y, -w1.y, ub));
 }
 
-template <int OUT>
+// HOPQ > 0: hop == 64*HOPQ, so frame B's element j is the stage element j + HOPQ of the same lane and the
+// two frames share their loads (32 + HOPQ instead of 64 per lane).  HOPQ == 0: any hop.
+template <int OUT, int HOPQ>
 __global__ void __launch_bounds__(kX2Warps * 32, 1)
 stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
@@ -232,13 +234,24 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
       while (!mbar_try_wait(bar, phase)) {}
       phase ^= 1;
       const float2* sa = reinterpret_cast<const float2*>(stage) + lane;
-      const float2* sb = reinterpret_cast<const float2*>(stage + g.hop) + lane;
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
-        window_stage1(a[r0], a[r1], sa[32 * j], sa[32 * (j + 16)], sb[32 * j], sb[32 * (j + 16)],
-                      s_win[lane + 32 * j], s_win[lane + 32 * (j + 16)]);
-      });
+      if constexpr (HOPQ > 0) {
+        float2 s[32 + HOPQ];
+        static_for<0, 32 + HOPQ>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = sa[32 * m]; });
+        static_for<0, 16>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
+          window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPQ], s[j + 16 + HOPQ], s_win[lane + 32 * j],
+                        s_win[lane + 32 * (j + 16)]);
+        });
+      } else {
+        const float2* sb = reinterpret_cast<const float2*>(stage + g.hop) + lane;
+        static_for<0, 16>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+          window_stage1(a[r0], a[r1], sa[32 * j], sa[32 * (j + 16)], sb[32 * j], sb[32 * (j + 16)],
+                        s_win[lane + 32 * j], s_win[lane + 32 * (j + 16)]);
+        });
+      }
     } else {
       const float* __restrict__ xa = g.pcm + cur.clip_a * g.clip_stride;
       const float* __restrict__ xb = g.pcm + cur.clip_b * g.clip_stride;

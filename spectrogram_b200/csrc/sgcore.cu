@@ -281,6 +281,7 @@ struct sg_engine {
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   bool w32_attr[4] = {false, false, false, false};   // per-device function attributes already set
   bool x2_attr[4] = {false, false, false, false};
+  bool x2g_attr[4] = {false, false, false, false};
   size_t smem_attr[4] = {0, 0, 0, 0};
   const char* last_kernel = "none";
   std::mutex mu;
@@ -320,17 +321,21 @@ int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const 
   const bool x2_ok = !(OUT == sg::kOutU8 || OUT == sg::kOutRgba8) || cfg.min_db >= -300.f;
   if (pl.n_fft == sg::kW32N && e->kernel_variant == 0 && x2_ok) {
     // packed two-frames-per-warp kernel (FFMA2), one persistent CTA per SM
-    if (!e->x2_attr[OUT]) {
-      SG_CUDA(cudaFuncSetAttribute(sg::stft_w32x2_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   sg::kX2SmemBytes));
-      e->x2_attr[OUT] = true;
-    }
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
     const long long pairs = (g.total_frames + 1) / 2;
     const long long ctas_needed = (pairs + sg::kX2Warps - 1) / sg::kX2Warps;
     const int grid = (int)std::min<long long>(ctas_needed, e->sm_count);
-    sg::stft_w32x2_kernel<OUT><<<grid, sg::kX2Warps * 32, sg::kX2SmemBytes, st>>>(g, wp, ep, (T*)out);
+    auto launch = [&](auto kern, bool& attr_done) -> int {
+      if (!attr_done) {
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sg::kX2SmemBytes));
+        attr_done = true;
+      }
+      kern<<<grid, sg::kX2Warps * 32, sg::kX2SmemBytes, st>>>(g, wp, ep, (T*)out);
+      return SG_OK;
+    };
+    if (g.hop == 512) SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 8>, e->x2_attr[OUT]));
+    else SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 0>, e->x2g_attr[OUT]));
     e->last_kernel = "warp32x32x2";
   } else if (pl.n_fft == sg::kW32N && e->kernel_variant != 1) {
     bool* attr_set = e->w32_attr;

@@ -173,13 +173,22 @@ def test_every_legal_size(engine, n_fft):
     check_all_outputs(engine, x, O.Config(n_fft=n_fft, hop=hop))
 
 
-@pytest.mark.parametrize("hop", [1, 3, 511, 513, 2048, 5000])
+@pytest.mark.parametrize("hop", [1, 3, 64, 128, 500, 511, 512, 513, 2048, 5000])
 def test_ragged_hops_n2048(engine, hop):
     """odd hops give 4-byte-aligned frames (the 8-byte fast loads do not apply), hop > n_fft skips samples"""
     rng = np.random.default_rng(hop)
     x = (0.3 * rng.standard_normal((3, 2048 + 9 * hop + 1))).astype(np.float32)
     for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
         check_all_outputs(engine, x, O.Config(hop=hop, align=align))
+
+
+def test_low_min_decibels_takes_the_exact_log_path(engine):
+    """minDecibels below -300 dB: subnormal powers matter, the packed kernel's flush-to-zero lg2 is not used"""
+    x = (1e-17 * np.random.default_rng(3).standard_normal((2, 8192))).astype(np.float32)
+    cfg = O.Config(min_db=-1000.0, max_db=0.0)
+    got = engine.spectrogram(x, opts_of(cfg))
+    assert engine.last_kernel == "warp32x32"
+    assert_bytes_close(got, O.spectrogram(x, cfg))
 
 
 def test_empty_and_short_inputs(engine):
