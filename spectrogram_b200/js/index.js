@@ -1,0 +1,162 @@
+'use strict';
+/*
+ * JavaScript facade of the B200 spectrogram engine: a drop-in for the AnalyserNode the reference
+ * builds in src/javascripts/UI/player.js:7-11 and polls in src/javascripts/3D/visualizer.js:346-368,
+ * plus the batched form of that loop.  Host code stays JavaScript; every number is produced by
+ * hand-written sm_100a CUDA kernels behind the thin Node-API addon (napi_shim.c -> libsgcore.so).
+ * There is no JavaScript or CPU fallback: if the addon or a B200 is missing, construction throws.
+ *
+ * Drop-in use in the reference (UI/player.js):
+ *     const { createAnalyser } = require('spectrogram-b200');
+ *     const analyser = createAnalyser();          // instead of context.createAnalyser()
+ *     analyser.fftSize = 2048;                     // player.js:10
+ *     analyser.smoothingTimeConstant = 0;          // player.js:11
+ *     ...
+ *     analyser.push(float32Samples);               // stands in for mix.connect(analyser), player.js:25
+ *     analyser.getByteFrequencyData(freqByteData); // visualizer.js:352,358 -- unchanged
+ */
+const path = require('path');
+
+let native;
+try {
+  native = require(path.join(__dirname, 'build', 'spectrogram.node'));
+} catch (err) {
+  const e = new Error('spectrogram-b200: native addon not built (run make in spectrogram_b200/js): ' + err.message);
+  e.code = 'ERR_ADDON_MISSING';
+  throw e;
+}
+
+// Web Audio raises DOMException(IndexSizeError); Node has no DOMException constructor for addons,
+// so the shim throws RangeError with code 'IndexSizeError' and the facade sets the name.
+function rethrow(err) {
+  if (err && err.code === 'IndexSizeError') err.name = 'IndexSizeError';
+  throw err;
+}
+function guard(fn) {
+  return function guarded() {
+    try {
+      return fn.apply(this, arguments);
+    } catch (err) {
+      return rethrow(err);
+    }
+  };
+}
+
+const engines = new Map();
+function engineFor(device) {
+  const d = device | 0;
+  if (!engines.has(d)) engines.set(d, native.engineCreate(d));
+  return engines.get(d);
+}
+
+class AnalyserNode {
+  constructor(options) {
+    const o = options || {};
+    this._engine = engineFor(o.device || 0);
+    this._h = native.analyserCreate(this._engine);
+    if (o.fftSize !== undefined) this.fftSize = o.fftSize;
+    if (o.minDecibels !== undefined) this.minDecibels = o.minDecibels;
+    if (o.maxDecibels !== undefined) this.maxDecibels = o.maxDecibels;
+    if (o.smoothingTimeConstant !== undefined) this.smoothingTimeConstant = o.smoothingTimeConstant;
+  }
+  get fftSize() { return native.analyserGet(this._h, 'fftSize'); }
+  set fftSize(v) { guard(native.analyserSet)(this._h, 'fftSize', Number(v)); }
+  get frequencyBinCount() { return native.analyserGet(this._h, 'frequencyBinCount'); }
+  get minDecibels() { return native.analyserGet(this._h, 'minDecibels'); }
+  set minDecibels(v) { guard(native.analyserSet)(this._h, 'minDecibels', Number(v)); }
+  get maxDecibels() { return native.analyserGet(this._h, 'maxDecibels'); }
+  set maxDecibels(v) { guard(native.analyserSet)(this._h, 'maxDecibels', Number(v)); }
+  get smoothingTimeConstant() { return native.analyserGet(this._h, 'smoothingTimeConstant'); }
+  set smoothingTimeConstant(v) { guard(native.analyserSet)(this._h, 'smoothingTimeConstant', Number(v)); }
+
+  // audio in: what the render thread does for a browser AnalyserNode
+  push(samples) {
+    if (!(samples instanceof Float32Array)) throw new TypeError('push() needs a Float32Array');
+    native.analyserPush(this._h, samples);
+  }
+  // graph plumbing is not part of the frame path; kept so call sites like player.js:25-26 run
+  connect(dest) { return dest; }
+  disconnect() {}
+
+  // getters write into the caller-owned typed array: min(array.length, frequencyBinCount) elements
+  getByteFrequencyData(array) {
+    if (!(array instanceof Uint8Array)) throw new TypeError('getByteFrequencyData needs a Uint8Array');
+    guard(native.getByteFrequencyData)(this._h, array);
+  }
+  getFloatFrequencyData(array) {
+    if (!(array instanceof Float32Array)) throw new TypeError('getFloatFrequencyData needs a Float32Array');
+    guard(native.getFloatFrequencyData)(this._h, array);
+  }
+  getByteTimeDomainData(array) {
+    if (!(array instanceof Uint8Array)) throw new TypeError('getByteTimeDomainData needs a Uint8Array');
+    guard(native.getByteTimeDomainData)(this._h, array);
+  }
+  getFloatTimeDomainData(array) {
+    if (!(array instanceof Float32Array)) throw new TypeError('getFloatTimeDomainData needs a Float32Array');
+    guard(native.getFloatTimeDomainData)(this._h, array);
+  }
+  close() {
+    if (this._h) native.analyserDestroy(this._h);
+    this._h = null;
+  }
+}
+
+const OUT_CTOR = { u8: Uint8Array, byte: Uint8Array, db: Float32Array, float: Float32Array, mag: Float32Array, rgba: Uint32Array, rgba8: Uint32Array };
+
+/**
+ * Batched frame path: pcm (Float32Array, nClips * clipLen samples, clip-major) ->
+ * { frames, bins, data } with data laid out [clip][frame][bin] (the row-per-frame layout the
+ * reference appends to its texture, visualizer.js:399-416).
+ * opts: { fftSize, hop, window, minDecibels, maxDecibels, smoothingTimeConstant, output, align,
+ *         nClips, device | devices }
+ * devices: [0, 1, ...] shards clips in contiguous blocks, one engine per GPU, results gathered by
+ * host copy into one typed array (no collective; shards are independent).
+ */
+function spectrogram(pcm, opts) {
+  if (!(pcm instanceof Float32Array)) throw new TypeError('pcm must be a Float32Array');
+  const o = Object.assign({ fftSize: 2048, hop: 512, output: 'u8' }, opts || {});
+  const nClips = o.nClips || 1;
+  if (pcm.length % nClips) throw new TypeError('pcm length is not a multiple of nClips');
+  const clipLen = pcm.length / nClips;
+  const frames = guard(native.numFrames)(o, clipLen);
+  const bins = o.fftSize / 2;
+  const Ctor = OUT_CTOR[o.output];
+  if (!Ctor) throw new TypeError('unknown output ' + o.output);
+  const data = new Ctor(nClips * frames * bins);
+  const devices = o.devices || [o.device || 0];
+  const G = devices.length;
+  for (let s = 0; s < G; s++) {
+    const lo = Math.floor((nClips * s) / G), hi = Math.floor((nClips * (s + 1)) / G);
+    if (hi <= lo) continue;
+    guard(native.stftBatch)(engineFor(devices[s]), pcm.subarray(lo * clipLen, hi * clipLen), hi - lo, clipLen, o,
+      data.subarray(lo * frames * bins, hi * frames * bins));
+  }
+  return { frames, bins, data };
+}
+
+class StreamBank {
+  constructor(nChannels, opts, maxChunk) {
+    this.opts = Object.assign({ fftSize: 1024, hop: 128, output: 'u8' }, opts || {});
+    this.nChannels = nChannels;
+    this.maxChunk = maxChunk || this.opts.hop;
+    this._h = guard(native.streamCreate)(engineFor(this.opts.device || 0), nChannels, this.opts, this.maxChunk);
+  }
+  // chunk: Float32Array [channel][chunkLen]; out: typed array [channel][chunkLen/hop][bins]
+  push(chunk, out, outRgba) {
+    const chunkLen = chunk.length / this.nChannels;
+    guard(native.streamPush)(this._h, chunk, chunkLen, out, outRgba);
+  }
+  close() {
+    if (this._h) native.streamDestroy(this._h);
+    this._h = null;
+  }
+}
+
+module.exports = {
+  AnalyserNode,
+  createAnalyser: (options) => new AnalyserNode(options),
+  spectrogram,
+  StreamBank,
+  colormapReference: () => native.colormapReference(),
+  deviceCount: () => native.deviceCount(),
+};
