@@ -42,6 +42,67 @@ smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
   state[idx] = s;
 }
 
+// ---- time-parallel form of the same recurrence for long clips with few (clip, bin) pairs -------------
+// The recurrence is linear with a constant coefficient, so a clip's frames are cut into chunks of
+// `chunk` frames:  (A) each chunk's zero-state response at its last frame, (B) a short sequential pass
+// over chunks that turns those into the true state at every chunk start, (C) the chunks re-run in
+// parallel from their true initial state, emitting dB / bytes.  Inputs are finite (the frame kernel
+// maps non-finite magnitudes to 0), so the [SPEC] non-finite rule cannot fire inside the scan.
+// carry: [n_clips][n_chunks][bins] float.
+__global__ void __launch_bounds__(256)
+scan_chunk_sums_kernel(const float* __restrict__ mags, float* __restrict__ carry, long long n_clips, long long frames,
+                       int bins, int chunk, long long n_chunks, double tau) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_clips * n_chunks * bins) return;
+  const int b = (int)(idx % bins);
+  const long long cj = idx / bins, clip = cj / n_chunks, j = cj - clip * n_chunks;
+  const long long t0 = j * chunk, t1 = min(frames, t0 + (long long)chunk);
+  const float* __restrict__ m = mags + clip * frames * bins + b;
+  const double k1 = 1.0 - tau;
+  double s = 0.0;
+  for (long long t = t0; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
+  carry[idx] = (float)s;
+}
+
+// carry[j] <- state at the START of chunk j (in place); state[clip][bin] holds the clip's initial state
+__global__ void __launch_bounds__(256)
+scan_chunk_carry_kernel(float* __restrict__ carry, const float* __restrict__ state, long long n_clips, long long frames,
+                        int bins, int chunk, long long n_chunks, double tau) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_clips * bins) return;
+  const long long clip = idx / bins;
+  const int b = (int)(idx - clip * bins);
+  float* __restrict__ c = carry + clip * n_chunks * bins + b;
+  double s = (double)state[idx];
+  for (long long j = 0; j < n_chunks; ++j) {
+    const long long len = min((long long)chunk, frames - j * chunk);
+    const double local = (double)c[j * bins];
+    c[j * bins] = (float)s;
+    s = pow(tau, (double)len) * s + local;
+  }
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(256)
+scan_chunk_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* __restrict__ out,
+                       const float* __restrict__ carry, float* __restrict__ state, long long n_clips, long long frames,
+                       int bins, int chunk, long long n_chunks, double tau, Epilogue ep) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_clips * n_chunks * bins) return;
+  const int b = (int)(idx % bins);
+  const long long cj = idx / bins, clip = cj / n_chunks, j = cj - clip * n_chunks;
+  const long long t0 = j * chunk, t1 = min(frames, t0 + (long long)chunk);
+  const float* __restrict__ m = mags + clip * frames * bins + b;
+  typename OutElem<OUT>::type* __restrict__ o = out + clip * frames * bins + b;
+  const double k1 = 1.0 - tau;
+  float s = carry[idx];
+  for (long long t = t0; t < t1; ++t) {
+    s = finite_or_zero((float)(tau * (double)s + k1 * (double)__ldg(m + t * bins)));
+    o[t * bins] = emit_mag<OUT>(s, ep);
+  }
+  if (j == n_chunks - 1) state[clip * bins + b] = s;
+}
+
 // re-emit a stored state vector (getByte/FloatFrequencyData called twice in one render quantum)
 template <int OUT>
 __global__ void emit_state_kernel(const float* __restrict__ state, typename OutElem<OUT>::type* __restrict__ out,

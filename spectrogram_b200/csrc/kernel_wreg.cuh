@@ -1,0 +1,216 @@
+// Register-resident batched real FFT for the power-of-two sizes n_fft = 256 ... 8192 that do not have
+// a dedicated kernel (north_star subsystem 2: "radix-4/radix-2 in shared memory with warp-level
+// butterflies for n = 256-8192").
+//
+// M = n_fft/2 complex points, T = M/32 threads per frame, 32 points per thread.  The network is
+// radix-2 decimation in time; its log2(M) stages are run in up to three register passes
+//   pass 1  stages 1-5      thread b owns z[b + T j], j < 32; compile-time twiddles
+//   pass 2  stages 6-10     min(log2(M)-5, 5) stages; lane-major twiddle table W_{32*2^u}^{32 p + k_a}
+//   pass 3  stages 11-12    only M = 2048, 4096
+// with the frame's working set in one shared-memory tile A[row][col], row stride 33 float2, updated in
+// place between passes (every access pattern below is bank-conflict free: lanes always walk a row).
+// After the last pass Z[k] sits at A[bitrev(k >> 5)][k & 31]; the real-input untangle, |X|^2, dB and
+// byte/colour epilogue follow as in kernel_w32.cuh.  tools/emulate_wreg.py checks the index algebra.
+//
+// Frames of a CTA (256 threads = 256/T frames) advance together; for T <= 32 a frame lives inside one
+// warp and only __syncwarp() is needed.
+#pragma once
+#include "common.cuh"
+#include "ct_math.cuh"
+#include "kernel_w32.cuh"   // bfly, bfly_const, dit_stage_const
+
+namespace sg {
+
+struct WregPlan {
+  const float* win;    // [n_fft]
+  const float2* tw2;   // [31][32]  W_{32*2^u}^{32 p + k_a}, row (2^(u-1) - 1 + p)      (any M)
+  const float2* tw3;   // [32][2^R3 - 1][32]  W_{1024*2^u}^{1024 p + 32 q + k_a}        (M = 2048, 4096)
+  const float2* ut;    // [M/2 + 1] W_n^k
+};
+
+constexpr int kWregThreads = 256;
+constexpr int kWregStride = 33;
+
+template <int LOG2M>
+struct WregShape {
+  static constexpr int M = 1 << LOG2M, N = 2 * M, T = M / 32, R = LOG2M - 5;
+  static constexpr int R2 = R < 5 ? R : 5, R3 = R - R2, L2 = 1 << R3;
+  static constexpr int S2 = 1 << R2, G2 = 32 / S2;   // pass 2: G2 sub-FFTs of S2 points per thread
+  static constexpr int S3 = 1 << R3, G3 = 32 / S3;   // pass 3
+  static constexpr int FPC = kWregThreads / T;       // frames per CTA
+  static constexpr int kTileF2 = T * kWregStride;    // float2 per frame tile
+  static constexpr int kFrameBytes = kTileF2 * 8 + M;   // tile + u8 staging
+  static constexpr int kSmemBytes = FPC * kFrameBytes;
+};
+
+// NS radix-2 DIT stages on the NS-point sub-array v[OFF .. OFF + 2^NS), twiddle row (2^(u-1)-1+p) of a
+// lane-major table (tw points at this thread's column)
+template <int NS, int OFF, int ROWSTRIDE>
+__device__ __forceinline__ void dit_stages_table(float2 (&v)[32], const float2* __restrict__ tw) {
+  static_for<1, NS + 1>([&](auto uu) {
+    constexpr int u = decltype(uu)::value, half = 1 << (u - 1), n = 1 << NS;
+    static_for<0, half>([&](auto pp) {
+      constexpr int p = decltype(pp)::value;
+      const float2 w = __ldg(tw + (half - 1 + p) * ROWSTRIDE);
+      static_for<0, n / (2 * half)>([&](auto bb) {
+        constexpr int i0 = OFF + decltype(bb)::value * 2 * half + p;
+        bfly(v[i0], v[i0 + half], w.x, w.y);
+      });
+    });
+  });
+}
+
+template <int LOG2M, int OUT>
+__global__ void __launch_bounds__(kWregThreads, 2)
+stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
+  using S = WregShape<LOG2M>;
+  using TO = typename OutElem<OUT>::type;
+  constexpr int M = S::M, N = S::N, T = S::T, R = S::R, R2 = S::R2, R3 = S::R3, L2 = S::L2;
+  extern __shared__ float4 smem_raw[];
+  const int tid = threadIdx.x, fs = tid / T, t = tid % T;
+  unsigned char* fbase = reinterpret_cast<unsigned char*>(smem_raw) + fs * S::kFrameBytes;
+  float2* A = reinterpret_cast<float2*>(fbase);
+  unsigned char* sb = fbase + S::kTileF2 * 8;
+  auto frame_sync = [] {
+    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
+  };
+  const long long groups = (g.total_frames + S::FPC - 1) / S::FPC;
+  for (long long gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    const long long f = gi * S::FPC + fs;
+    const bool live = f < g.total_frames;
+    const long long fc = live ? f : g.total_frames - 1;     // idle slots recompute the last frame, store nothing
+    const long long clip = fc / g.frames_per_clip, tt = fc - clip * g.frames_per_clip;
+    const long long start = g.start0 + tt * g.hop;
+    const float* __restrict__ x = g.pcm + clip * g.clip_stride;
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*>(pl.win);
+
+    // ---- pass 1: load + window + stages 1-5
+    float2 v[32];
+    const bool interior = start >= 0 && start + N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
+    if (interior) {
+      const float2* __restrict__ src = reinterpret_cast<const float2*>(x + start) + t;
+      static_for<0, 32>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float2 s = __ldg(src + T * j), w = __ldg(win2 + t + T * j);
+        v[bitrev(j, 5)] = make_float2(s.x * w.x, s.y * w.y);
+      });
+    } else {
+      static_for<0, 32>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const long long s0 = start + 2 * (t + T * j), s1 = s0 + 1;
+        const float a0 = (s0 >= 0 && s0 < g.clip_len) ? __ldg(x + s0) : 0.f;
+        const float a1 = (s1 >= 0 && s1 < g.clip_len) ? __ldg(x + s1) : 0.f;
+        const float2 w = __ldg(win2 + t + T * j);
+        v[bitrev(j, 5)] = make_float2(a0 * w.x, a1 * w.y);
+      });
+    }
+    dit_stage_const<1>(v);
+    dit_stage_const<2>(v);
+    dit_stage_const<3>(v);
+    dit_stage_const<4>(v);
+    dit_stage_const<5>(v);
+    static_for<0, 32>([&](auto kk) { constexpr int k = decltype(kk)::value; A[t * kWregStride + k] = v[k]; });
+    frame_sync();
+
+    // ---- pass 2: stages 6 .. 5+R2; sub-FFT c: column k_a, rows bitrev(q)*L2 + hi2'
+    if constexpr (R2 > 0) {
+      const int hi2p = (R > 5) ? (t >> 5) : 0;
+      static_for<0, S::G2>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int ka = (R > 5) ? (t & 31) : (t + T * c);
+        static_for<0, S::S2>([&](auto qq) {
+          constexpr int q = decltype(qq)::value;
+          v[c * S::S2 + q] = A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka];
+        });
+      });
+      static_for<0, S::G2>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int ka = (R > 5) ? (t & 31) : (t + T * c);
+        dit_stages_table<R2, c * S::S2, 32>(v, pl.tw2 + ka);
+      });
+      static_for<0, S::G2>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int ka = (R > 5) ? (t & 31) : (t + T * c);
+        static_for<0, S::S2>([&](auto qq) {
+          constexpr int q = decltype(qq)::value;
+          A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka] = v[c * S::S2 + q];
+        });
+      });
+      frame_sync();
+    }
+
+    // ---- pass 3: stages 11 .. 10+R3; sub-FFT c: column k_a, q = g*G3 + c, rows bitrev5(q)*L2 + bitrev(h)
+    if constexpr (R3 > 0) {
+      const int ka = t & 31, gq = t >> 5;
+      const int brg = (int)(__brev((unsigned)gq) >> (32 - R3));
+      static_for<0, S::G3>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;   // bitrev5(gq*G3 + c) * L2
+        static_for<0, S::S3>([&](auto hh) {
+          constexpr int h = decltype(hh)::value;
+          v[c * S::S3 + h] = A[(row0 + bitrev(h, R3)) * kWregStride + ka];
+        });
+      });
+      static_for<0, S::G3>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int q = gq * S::G3 + c;
+        dit_stages_table<R3, c * S::S3, 32>(v, pl.tw3 + (q * (S::S3 - 1)) * 32 + ka);
+      });
+      static_for<0, S::G3>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;
+        static_for<0, S::S3>([&](auto hh) {
+          constexpr int h = decltype(hh)::value;
+          A[(row0 + bitrev(h, R3)) * kWregStride + ka] = v[c * S::S3 + h];
+        });
+      });
+      frame_sync();
+    }
+
+    // ---- untangle + epilogue: thread t owns k = t + T i (i < 16) and the mirror bins M - k
+    auto zat = [&](int k) { return A[(int)(__brev((unsigned)(k >> 5)) >> (32 - R)) * kWregStride + (k & 31)]; };
+    TO* __restrict__ row = out + fc * (long long)M;
+    static_for<0, 16>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      const int k = t + T * i;
+      const int km = (M - k) & (M - 1);
+      const float2 zk = zat(k), zm = zat(km);
+      const float2 w = __ldg(pl.ut + k);
+      const float ex = zk.x + zm.x, ey = zk.y - zm.y;       // 2E
+      const float ox = zk.y + zm.y, oy = zm.x - zk.x;       // 2O
+      const float xr = fmaf(ox, w.x, fmaf(-oy, w.y, ex));   // 2X[k]
+      const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
+      const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
+      const float yi = fmaf(2.f, ey, -xi);
+      const float pk = fmaf(xr, xr, xi * xi);
+      float pm = fmaf(yr, yr, yi * yi);
+      int mk = M - k;
+      if constexpr (i == 0) {
+        if (t == 0) {   // the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2]
+          const float2 zh = zat(M / 2);
+          mk = M / 2;
+          pm = 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
+        }
+      }
+      if constexpr (OUT == kOutU8) {
+        sb[k] = emit_power<OUT>(pk, ep);
+        sb[mk] = emit_power<OUT>(pm, ep);
+      } else if (live) {
+        row[k] = emit_power<OUT>(pk, ep);
+        row[mk] = emit_power<OUT>(pm, ep);
+      }
+    });
+    frame_sync();
+    if constexpr (OUT == kOutU8) {
+      if (live) {
+        const uint4* s16 = reinterpret_cast<const uint4*>(sb);
+        uint4* r16 = reinterpret_cast<uint4*>(row);
+        r16[t] = s16[t];
+        r16[T + t] = s16[T + t];
+      }
+      frame_sync();
+    }
+  }
+}
+
+}  // namespace sg

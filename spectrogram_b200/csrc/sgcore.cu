@@ -20,6 +20,7 @@
 #include "kernel_smem.cuh"
 #include "kernel_w32.cuh"
 #include "kernel_w32x2.cuh"
+#include "kernel_wreg.cuh"
 
 namespace {
 
@@ -66,10 +67,12 @@ struct Plan {
   float2* tw = nullptr;
   float2* ut = nullptr;
   int* pos = nullptr;
-  float2* w32_tw2 = nullptr;  // only n_fft == 2048
-  float2* w32_ut = nullptr;
+  float2* w32_tw2 = nullptr;  // lane-major stage 6-10 twiddles (powers of two, 256 <= n_fft <= 8192)
+  float2* w32_ut = nullptr;   // only n_fft == 2048
+  float2* wreg_tw3 = nullptr; // lane-major stage 11-12 twiddles (n_fft 4096, 8192)
+  int log2m = 0;              // log2(n_fft/2) when n_fft is a power of two, else 0
   void release() {
-    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut);
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3);
   }
 };
 
@@ -140,17 +143,37 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
   SG_TRY(upload(&p.tw, tw));
   SG_TRY(upload(&p.ut, ut));
   SG_TRY(upload(&p.pos, pos));
-  if (n == sg::kW32N) {
-    std::vector<float2> tw2(31 * 32), ut32(16 * 32);
+  if ((m & (m - 1)) == 0) {
+    while ((1 << p.log2m) < m) ++p.log2m;
+  }
+  if (p.log2m >= 7 && p.log2m <= 12) {
+    std::vector<float2> tw2(31 * 32);
     for (int u = 1; u <= 5; ++u) {
       const int half = 1 << (u - 1);
       for (int q = 0; q < half; ++q)
         for (int lane = 0; lane < 32; ++lane)
           tw2[(half - 1 + q) * 32 + lane] = expi((double)(q * 32 + lane) / (32.0 * 2 * half));
     }
+    SG_TRY(upload(&p.w32_tw2, tw2));
+    const int r3 = p.log2m - 10;
+    if (r3 > 0) {
+      const int s3 = 1 << r3;
+      std::vector<float2> tw3((size_t)32 * (s3 - 1) * 32);
+      for (int q = 0; q < 32; ++q)
+        for (int u = 1; u <= r3; ++u) {
+          const int half = 1 << (u - 1);
+          for (int pp = 0; pp < half; ++pp)
+            for (int ka = 0; ka < 32; ++ka)
+              tw3[((size_t)q * (s3 - 1) + half - 1 + pp) * 32 + ka] =
+                  expi((double)(pp * 1024 + q * 32 + ka) / (1024.0 * 2 * half));
+        }
+      SG_TRY(upload(&p.wreg_tw3, tw3));
+    }
+  }
+  if (n == sg::kW32N) {
+    std::vector<float2> ut32(16 * 32);
     for (int i = 0; i < 16; ++i)
       for (int lane = 0; lane < 32; ++lane) ut32[i * 32 + lane] = expi((double)(lane + 32 * i) / n);
-    SG_TRY(upload(&p.w32_tw2, tw2));
     SG_TRY(upload(&p.w32_ut, ut32));
   }
   return SG_OK;
@@ -275,13 +298,14 @@ struct sg_engine {
   std::map<PlanKey, Plan> plans;
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
-  DevBuf scratch_mag, scratch_state, d_in, d_out;
+  DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   bool w32_attr[4] = {false, false, false, false};   // per-device function attributes already set
   bool x2_attr[4] = {false, false, false, false};
   bool x2g_attr[4] = {false, false, false, false};
+  bool wreg_attr[13][4] = {};
   size_t smem_attr[4] = {0, 0, 0, 0};
   const char* last_kernel = "none";
   std::mutex mu;
@@ -337,7 +361,7 @@ int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const 
     if (g.hop == 512) SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 8>, e->x2_attr[OUT]));
     else SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 0>, e->x2g_attr[OUT]));
     e->last_kernel = "warp32x32x2";
-  } else if (pl.n_fft == sg::kW32N && e->kernel_variant != 1) {
+  } else if (pl.n_fft == sg::kW32N && e->kernel_variant != 1 && e->kernel_variant != 3) {
     bool* attr_set = e->w32_attr;
     if (!attr_set[OUT]) {
       SG_CUDA(cudaFuncSetAttribute(sg::stft_w32_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -350,6 +374,31 @@ int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const 
     const int grid = (int)std::min<long long>(ctas_needed, 2LL * e->sm_count);
     sg::stft_w32_kernel<OUT><<<grid, sg::kW32Warps * 32, sg::kW32SmemBytes, st>>>(g, wp, ep, (T*)out);
     e->last_kernel = "warp32x32";
+  } else if (pl.log2m >= 7 && pl.log2m <= 12 && e->kernel_variant != 1) {
+    const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
+    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+    auto launch = [&](auto shape_tag) -> int {
+      constexpr int LM = decltype(shape_tag)::value;
+      using S = sg::WregShape<LM>;
+      bool& done = e->wreg_attr[LM][OUT];
+      if (!done) {
+        SG_CUDA(cudaFuncSetAttribute(sg::stft_wreg_kernel<LM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
+        done = true;
+      }
+      const long long groups = (g.total_frames + S::FPC - 1) / S::FPC;
+      const int grid = (int)std::min<long long>(groups, 2LL * e->sm_count);
+      sg::stft_wreg_kernel<LM, OUT><<<grid, sg::kWregThreads, S::kSmemBytes, st>>>(g, wp, ep, (T*)out);
+      return SG_OK;
+    };
+    switch (pl.log2m) {
+      case 7: SG_TRY(launch(std::integral_constant<int, 7>{})); break;
+      case 8: SG_TRY(launch(std::integral_constant<int, 8>{})); break;
+      case 9: SG_TRY(launch(std::integral_constant<int, 9>{})); break;
+      case 10: SG_TRY(launch(std::integral_constant<int, 10>{})); break;
+      case 11: SG_TRY(launch(std::integral_constant<int, 11>{})); break;
+      default: SG_TRY(launch(std::integral_constant<int, 12>{})); break;
+    }
+    e->last_kernel = "wreg";
   } else {
     sg::SmemPlan sp;
     sp.win = pl.win; sp.tw = pl.tw; sp.ut = pl.ut; sp.pos = pl.pos; sp.m = pl.m;
@@ -390,6 +439,24 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
   using T = typename sg::OutElem<OUT>::type;
   const long long n = n_clips * bins;
   if (n <= 0 || frames <= 0) return SG_OK;
+  // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run
+  const long long want_threads = 2048LL * e->sm_count / 4;
+  if (n < want_threads && frames >= 256) {
+    const int chunk = (int)std::max<long long>(32, std::min<long long>(1024, frames * n / want_threads));
+    const long long n_chunks = (frames + chunk - 1) / chunk;
+    SG_TRY(e->scratch_carry.reserve((size_t)n * n_chunks * sizeof(float)));
+    float* carry = (float*)e->scratch_carry.p;
+    const long long nt = n * n_chunks;
+    sg::scan_chunk_sums_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, carry, n_clips, frames, bins, chunk,
+                                                                           n_chunks, tau);
+    sg::scan_chunk_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry, state, n_clips, frames, bins, chunk,
+                                                                            n_chunks, tau);
+    sg::scan_chunk_emit_kernel<OUT><<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, (T*)out, carry, state, n_clips,
+                                                                                frames, bins, chunk, n_chunks, tau, ep);
+    e->launches += 3;
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+  }
   sg::smooth_emit_kernel<OUT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mags, (T*)out, state, n_clips, frames,
                                                                           bins, tau, ep);
   e->launches++;
@@ -528,7 +595,7 @@ int sg_engine_destroy(sg_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
-  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->d_in.release(); e->d_out.release();
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->d_in.release(); e->d_out.release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
   delete e;
@@ -539,8 +606,8 @@ int sg_engine_device(const sg_engine* e) { return e ? e->device : SG_ERR_INVALID
 int64_t sg_engine_launch_count(const sg_engine* e) { return e ? e->launches : 0; }
 const char* sg_engine_last_kernel(const sg_engine* e) { return e ? e->last_kernel : "none"; }
 int sg_engine_set_kernel_variant(sg_engine* e, int variant) {
-  if (!e || variant < 0 || variant > 2)
-    return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto), 1 (generic smem) or 2 (one frame per warp)");
+  if (!e || variant < 0 || variant > 3)
+    return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto), 1 (generic smem), 2 (one frame per warp) or 3 (register family)");
   e->kernel_variant = variant;
   return SG_OK;
 }
