@@ -7,18 +7,9 @@
 // shared-memory passes bind; this kernel is the coverage path, not the headline path.
 #pragma once
 #include "common.cuh"
+#include "plans.cuh"
 
 namespace sg {
-
-struct SmemPlan {
-  const float* win;    // [n_fft]
-  const float2* tw;    // [m]      W_m^k
-  const float2* ut;    // [m/2+1]  W_n^k
-  const int* pos;      // [m]      position of Z[k] after the in-place DIF (digit reversal)
-  int m;               // n_fft/2
-  int nstage;
-  int radix[16];
-};
 
 template <int R>
 __device__ __forceinline__ void dft_small(float2 (&x)[R]) {

@@ -21,23 +21,16 @@
 // per frame), so HBM fraction is reported together with the issue-slot budget.
 #pragma once
 #include "common.cuh"
+#include "plans.cuh"
 #include "ct_math.cuh"
 
 namespace sg {
 
-constexpr int kW32N = 2048;
-constexpr int kW32M = 1024;
 constexpr int kW32Stride = 34;                       // float2 per exchange-tile row
 constexpr int kW32TileBytes = 32 * kW32Stride * 8;   // 8704 B per warp
 constexpr int kW32Warps = 8;
 constexpr int kW32TableBytes = kW32N * 4 + 31 * 32 * 8 + 16 * 32 * 8;  // window + tw2 + ut
 constexpr int kW32SmemBytes = kW32TableBytes + kW32Warps * kW32TileBytes;
-
-struct W32Plan {
-  const float* win;    // [2048]
-  const float2* tw2;   // [31][32]: stage u (1..5), p < 2^(u-1): W_{32*2^u}^{32 p + lane}
-  const float2* ut;    // [16][32]: W_2048^{lane + 32 i}
-};
 
 // x' = x + w*y ; y' = x - w*y = 2x - x'   (6 FMA-pipe instructions)
 __device__ __forceinline__ void bfly(float2& x, float2& y, float wr, float wi) {

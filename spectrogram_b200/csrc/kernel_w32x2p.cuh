@@ -1,0 +1,335 @@
+// Headline kernel, register-pipelined form: n_fft = 2048 (the reference's fftSize, UI/player.js:10),
+// hop = 512, one warp per PAIR of consecutive frames, packed FP32 arithmetic (FFMA2 / FADD2).
+//
+// Same arithmetic network as kernel_w32x2.cuh (1024-point complex radix-2 DIT split 5 + 5, real-FFT
+// untangle, dB / byte epilogue).  That kernel is bound by the shared-memory data path (~820 wavefronts per
+// frame pair against ~2400 FP32-pipe cycles per scheduler); this one moves everything that does not have
+// to cross lanes out of shared memory:
+//   loader     the 2560 samples a frame pair covers are read straight into registers (40 coalesced
+//              8-byte loads per lane, the two frames share 24 of every 32), issued for the NEXT pair
+//              during the untangle -- as the FFT registers die -- so the HBM/L2 latency hides behind
+//              the untangle and the dB / byte epilogue; one lane also asks L2 for the pair after that
+//              (cp.async.bulk.prefetch.L2).  No shared-memory stage at all.
+//   exchange   the 32x32 transpose keeps two planes (re, im) of (frame A, frame B) pairs with row pairs
+//              interleaved: 64 STS.64 + 32 LDS.128, bank-conflict free both ways, operands already in
+//              the register pairs/quads the packed arithmetic uses (no moves)
+//   twiddles   pass 2 builds W_{2^u}^p * W_{32*2^u}^lane from five per-lane bases and compile-time
+//              constants (scalar FMAs shared by both frames) instead of a 31-row table
+//   untangle   Z[1024-k] lives in the partner lane (32 - lane): 64 warp shuffles replace the
+//              shared-memory round trip of the upper half
+//   non-finite [SPEC] "NaN/Inf -> 0" is decided once per frame (a non-finite sample poisons every bin
+//              of its frame), folded into the byte scale, instead of once per bin
+// ~550 shared-memory wavefronts per pair.  Frames the fast loader cannot express (clip edges / zero
+// history, pairs that straddle clips, odd alignment) take guarded loads.
+#pragma once
+#include "common.cuh"
+#include "ct_math.cuh"
+#include "kernel_w32.cuh"
+#include "kernel_w32x2.cuh"
+
+namespace sg {
+
+constexpr int kXpStride = 33;                               // 16-byte units per row PAIR of one plane
+constexpr int kXpPlaneBytes = 2 * 16 * kXpStride * 16;      // re plane + im plane: 16896 B
+constexpr int kXpBytesStage = 2 * kW32M;                    // u8 staging: 1024 (A,B) byte pairs
+constexpr int kXpWarpBytes = kXpPlaneBytes;                 // the byte stage reuses the planes after the exchange
+constexpr int kXpTableBytes = kW32M * 8 + 5 * 32 * 8 + 16 * 32 * 8;   // window + 5 base twiddles + untangle
+constexpr int kXpLoadSteps = 16;   // the next pair's 40 loads are spread over this many untangle steps
+template <int NW>
+struct XpShape {
+  static constexpr int kSmemBytes = kXpTableBytes + NW * kXpWarpBytes;
+  static constexpr int kMaxRegs = NW <= 8 ? 255 : (65536 / (NW * 32)) / 8 * 8;
+};
+
+// (wx, wy) = W_N^P * base, reusing W^{P + N/4} = -i W^P
+template <int P, int N>
+__device__ __forceinline__ float2 twiddle_times(float2 b) {
+  if constexpr (P == 0) {
+    return b;
+  } else if constexpr (4 * P >= N) {
+    const float2 t = twiddle_times<P - N / 4, N>(b);
+    return make_float2(t.y, -t.x);
+  } else {
+    constexpr float cx = Twiddle<P, N>::re, cy = Twiddle<P, N>::im;
+    return make_float2(fmaf(cx, b.x, -cy * b.y), fmaf(cx, b.y, cy * b.x));
+  }
+}
+
+// stage U (1..5) of pass 2: butterflies (i0, i0 + half), twiddle W_{2 half}^p * base
+template <int U>
+__device__ __forceinline__ void dit2_stage_gen(C2 (&a)[32], float2 base) {
+  constexpr int half = 1 << (U - 1);
+  static_for<0, half>([&](auto pp) {
+    constexpr int p = decltype(pp)::value;
+    const float2 w = twiddle_times<p, 2 * half>(base);
+    static_for<0, 16 / half>([&](auto bb) {
+      constexpr int i0 = decltype(bb)::value * 2 * half + p;
+      bfly2(a[i0], a[i0 + half], w.x, w.y);
+    });
+  });
+}
+
+// volatile: the loads stay where they are written (interleaved with the untangle)
+__device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Loop state is kept small (the FFT needs nearly the whole register file): a pair is (clip, t) of frame A.
+struct PairP {
+  long long fa;   // global index of frame A; frame B = fa + 1
+  int clip, t;    // clip and in-clip index of frame A
+};
+
+// both frames inside one clip, no zero fill, 8-byte aligned first sample
+__device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p) {
+  const long long start_a = g.start0 + (long long)p.t * 512;
+  return p.fa + 1 < g.total_frames && p.t + 1 < g.frames_per_clip && start_a >= 0 &&
+         start_a + 512 + kW32N <= g.clip_len &&
+         ((reinterpret_cast<uintptr_t>(g.pcm + p.clip * g.clip_stride + start_a) & 7) == 0);
+}
+__device__ __forceinline__ const float2* pair_src(const FrameGeom& g, const PairP& p, int lane) {
+  return reinterpret_cast<const float2*>(g.pcm + p.clip * g.clip_stride + g.start0 + (long long)p.t * 512) + lane;
+}
+
+template <int OUT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
+stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
+  using T = typename OutElem<OUT>::type;
+  extern __shared__ float4 smem_raw[];
+  float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
+  float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
+  float2* s_ut = s_twb + 5 * 32;                                       // [16][32] W_2048^{lane + 32 i}
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(s_ut + 16 * 32) + warp * kXpWarpBytes;
+  float4* xp = reinterpret_cast<float4*>(wbase);                       // exchange planes
+  uint16_t* sb16 = reinterpret_cast<uint16_t*>(wbase);   // aliases the planes: written after the exchange is read
+
+  {
+    const float2* w2 = reinterpret_cast<const float2*>(pl.win);
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+      const int j = i >> 5, l = i & 31;
+      const float2 lo = __ldg(w2 + l + 32 * j), hi = __ldg(w2 + l + 32 * (j + 16));
+      s_win4[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    for (int i = threadIdx.x; i < 5 * 32; i += blockDim.x) {
+      const int u = i >> 5, l = i & 31;
+      s_twb[i] = __ldg(pl.tw2 + ((1 << u) - 1) * 32 + l);
+    }
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) s_ut[i] = __ldg(pl.ut + i);
+  }
+  __syncthreads();
+
+  const int fpc = (int)g.frames_per_clip;
+  const int step = 2 * gridDim.x * NW;                 // frames between a warp's consecutive pairs
+  const int step_clip = step / fpc, step_t = step - step_clip * fpc;
+  PairP cur;
+  cur.fa = 2 * ((long long)blockIdx.x * NW + warp);
+  if (cur.fa >= g.total_frames) return;
+  cur.clip = (int)(cur.fa / fpc);
+  cur.t = (int)(cur.fa - (long long)cur.clip * fpc);
+  bool cur_fast = pair_is_fast(g, cur);
+  const int partner = (32 - lane) & 31;
+  const bool lane0 = lane == 0;
+
+  float2 s[40];   // samples of the current pair (fast path): element m = float2 #(lane + 32 m) of the span
+  const float2* idle_src = reinterpret_cast<const float2*>(pl.win) + lane;   // 4096 readable floats (build_plan)
+  {
+    // loads are unconditional (a pair the fast loader cannot express reads the idle table and ignores it):
+    // the destination registers are the loop-carried sample registers themselves, nothing waits on a copy
+    const float2* src = cur_fast ? pair_src(g, cur, lane) : idle_src;
+    static_for<0, 40>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
+  }
+
+  while (true) {
+    // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
+    C2 a[32];
+    if (cur_fast) {
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
+        const float4 w = s_win4[j * 32 + lane];
+        window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + 8], s[j + 24], make_float2(w.x, w.y), make_float2(w.z, w.w));
+      });
+    } else {
+      // clip edges / zero history / the last frame of a clip paired with the first of the next
+      const bool has_b = cur.fa + 1 < g.total_frames;
+      int clip_b = cur.clip, tb = cur.t;
+      if (has_b) { if (cur.t + 1 == fpc) { ++clip_b; tb = 0; } else ++tb; }
+      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
+      const float* __restrict__ xb = g.pcm + clip_b * g.clip_stride;
+      const long long start_a = g.start0 + (long long)cur.t * 512, start_b = g.start0 + (long long)tb * 512;
+      auto ld = [&](const float* __restrict__ x, long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(x + q) : 0.f; };
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+        const long long o0 = 2 * (lane + 32 * j), o1 = 2 * (lane + 32 * (j + 16));
+        const float4 w = s_win4[j * 32 + lane];
+        window_stage1(a[r0], a[r1], make_float2(ld(xa, start_a + o0), ld(xa, start_a + o0 + 1)),
+                      make_float2(ld(xa, start_a + o1), ld(xa, start_a + o1 + 1)),
+                      make_float2(ld(xb, start_b + o0), ld(xb, start_b + o0 + 1)),
+                      make_float2(ld(xb, start_b + o1), ld(xb, start_b + o1 + 1)), make_float2(w.x, w.y),
+                      make_float2(w.z, w.w));
+      });
+    }
+
+    // ---- pass 1: stages 2-5 in registers, compile-time twiddles
+    dit2_stage_const<2>(a);
+    dit2_stage_const<3>(a);
+    dit2_stage_const<4>(a);
+    dit2_stage_const<5>(a);
+
+    // ---- exchange (32x32 transpose).  Each plane (re, im) keeps rows 2j and 2j+1 interleaved in 16-byte units:
+    //      unit (j, col) = [row 2j | row 2j+1].  Lane b stores its element k_a as one 8-byte half (STS.64, the 16
+    //      lanes of a half-warp fill 8 whole units: conflict free); lane a then reads column a of a row pair with
+    //      one LDS.128 -- rows b = 2j, 2j+1 hold q = bitrev4(j), bitrev4(j) + 16.
+    {
+      float2* wre = reinterpret_cast<float2*>(xp) + ((lane >> 1) * kXpStride) * 2 + (lane & 1);
+      float2* wim = wre + 16 * kXpStride * 2;
+      static_for<0, 32>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        wre[2 * q] = a[q].re.v;
+        wim[2 * q] = a[q].im.v;
+      });
+      asm volatile("bar.sync %0, 32;" ::"r"(warp + 1) : "memory");
+      const float4* rre = xp + lane;
+      const float4* rim = rre + 16 * kXpStride;
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int q0 = bitrev(j, 4);
+        const float4 vr = rre[j * kXpStride], vi = rim[j * kXpStride];
+        a[q0].re = P2(vr.x, vr.y); a[q0 + 16].re = P2(vr.z, vr.w);
+        a[q0].im = P2(vi.x, vi.y); a[q0 + 16].im = P2(vi.z, vi.w);
+      });
+      __syncwarp();
+    }
+
+    // ---- pass 2: stages 6-10, twiddles from the five per-lane bases
+    dit2_stage_gen<1>(a, s_twb[0 * 32 + lane]);
+    dit2_stage_gen<2>(a, s_twb[1 * 32 + lane]);
+    dit2_stage_gen<3>(a, s_twb[2 * 32 + lane]);
+    dit2_stage_gen<4>(a, s_twb[3 * 32 + lane]);
+    dit2_stage_gen<5>(a, s_twb[4 * 32 + lane]);
+    // now a[i] = Z[lane + 32 i] of both frames
+
+    // a non-finite sample makes every Z of its frame non-finite: one test per frame. byte scale -> NaN -> byte 0
+    const P2 poison = fma2(a[0].re, bc(0.f), mul2(a[0].im, bc(0.f)));   // 0 or NaN per frame
+
+    // ---- next pair: geometry now, its 40 loads interleaved with the untangle below (registers free up as the
+    //      untangle consumes Z), so HBM/L2 latency hides behind the untangle and the epilogue
+    PairP nxt;
+    nxt.fa = cur.fa + step; nxt.clip = cur.clip + step_clip; nxt.t = cur.t + step_t;
+    if (nxt.t >= fpc) { nxt.t -= fpc; ++nxt.clip; }
+    const bool has_next = nxt.fa < g.total_frames;
+    const bool nxt_fast = has_next && pair_is_fast(g, nxt);
+    const float2* nsrc = nxt_fast ? pair_src(g, nxt, lane) : idle_src;
+
+    // ---- untangle.  Z[1024 - k] for k = lane + 32 i is the partner lane's a[31 - i] (lane 0: its own a[32 - i]).
+    //      First fetch every mirror IN PLACE (a[31 - i] <- partner's a[31 - i]; descending i keeps lane 0's own
+    //      a[32 - i] intact until it is read), so the arithmetic below is pure register work with no shuffle in
+    //      its dependency chains.  Bin 512 = conj Z[512] (lane 0's a[16]) is taken before a[16] is replaced.
+    const P2 p512 = mul2(bc(4.f), fma2(a[16].re, a[16].re, mul2(a[16].im, a[16].im)));
+    static_for<0, 16>([&](auto ii) {
+      constexpr int i = 15 - decltype(ii)::value;
+      constexpr int src = 31 - i, own = (32 - i) & 31;
+      const float mra = __shfl_sync(0xffffffffu, a[src].re.v.x, partner);
+      const float mrb = __shfl_sync(0xffffffffu, a[src].re.v.y, partner);
+      const float mia = __shfl_sync(0xffffffffu, a[src].im.v.x, partner);
+      const float mib = __shfl_sync(0xffffffffu, a[src].im.v.y, partner);
+      a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
+      a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
+    });
+    P2 pk[16], pm[16];
+    static_for<0, 16>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      const P2 zmr = a[31 - i].re, zmi = a[31 - i].im;
+      const float2 w = s_ut[i * 32 + lane];
+      const C2 zk = a[i];
+      const P2 ex = add2(zk.re, zmr), ey = add2(zk.im, neg(zmi));          // 2E
+      const P2 ox = add2(zk.im, zmi), oy = add2(zmr, neg(zk.re));          // 2O
+      const P2 xr = fma2(ox, bc(w.x), fma2(oy, bc(-w.y), ex));             // 2X[k]
+      const P2 xi = fma2(ox, bc(w.y), fma2(oy, bc(w.x), ey));
+      const P2 yr = fma2(ex, bc(2.f), neg(xr));                            // 2 conj X[1024-k]
+      const P2 yi = fma2(ey, bc(2.f), neg(xi));
+      pk[i] = fma2(xr, xr, mul2(xi, xi));
+      pm[i] = fma2(yr, yr, mul2(yi, yi));
+      if constexpr (i == 0) {
+        // lane 0: the mirror of k = 0 is the Nyquist bin (dropped); its slot carries bin 512
+        pm[0] = P2(lane0 ? p512.v.x : pm[0].v.x, lane0 ? p512.v.y : pm[0].v.y);
+      }
+      // this step's share of the next pair's loads
+      if constexpr (i < kXpLoadSteps) {
+        static_for<(40 * i) / kXpLoadSteps, (40 * (i + 1)) / kXpLoadSteps>([&](auto mm) {
+          constexpr int m = decltype(mm)::value;
+          s[m] = ldg_nc_f2(nsrc + 32 * m);
+        });
+      }
+    });
+    if (nxt_fast && lane0) {
+      // ask L2 for the pair after the next one (one bulk prefetch instruction per pair)
+      PairP n2;
+      n2.fa = nxt.fa + step; n2.clip = nxt.clip + step_clip; n2.t = nxt.t + step_t;
+      if (n2.t >= fpc) { n2.t -= fpc; ++n2.clip; }
+      const float2* p2 = pair_src(g, n2, 0);
+      if (n2.fa + 1 < g.total_frames && n2.t + 1 < fpc && ((reinterpret_cast<uintptr_t>(p2) & 15) == 0))
+        prefetch_l2_bulk(p2, (kW32N + 512) * 4);
+    }
+
+    // ---- epilogue
+    const bool has_b_out = cur.fa + 1 < g.total_frames;
+    T* __restrict__ row_a = out + cur.fa * (long long)kW32M;
+    T* __restrict__ row_b = row_a + kW32M;   // frame B is the next global frame
+    if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
+      const P2 scale = add2(bc(ep.byte_a), poison);
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int k = lane + 32 * i;
+        int mk = kW32M - k;
+        if constexpr (i == 0) { if (lane0) mk = 512; }
+        const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), scale, bc(ep.byte_b));
+        const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), scale, bc(ep.byte_b));
+        const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
+        const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
+        if constexpr (OUT == kOutU8) {
+          sb16[k] = (uint16_t)(ka | (kb << 8));
+          sb16[mk] = (uint16_t)(ma | (mb << 8));
+        } else {
+          row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
+          if (has_b_out) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
+        }
+      });
+      if constexpr (OUT == kOutU8) {
+        __syncwarp();
+        // de-interleave the (A,B) byte pairs: 8 bins per lane per round, 8-byte coalesced row stores
+        const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
+        uint2* ra = reinterpret_cast<uint2*>(row_a);
+        uint2* rb = reinterpret_cast<uint2*>(row_b);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = s16[c * 32 + lane];
+          ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+          if (has_b_out) rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+        }
+      }
+    } else {
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int k = lane + 32 * i;
+        int mk = kW32M - k;
+        if constexpr (i == 0) { if (lane0) mk = 512; }
+        row_a[k] = emit_power<OUT>(pk[i].v.x, ep); row_a[mk] = emit_power<OUT>(pm[i].v.x, ep);
+        if (has_b_out) { row_b[k] = emit_power<OUT>(pk[i].v.y, ep); row_b[mk] = emit_power<OUT>(pm[i].v.y, ep); }
+      });
+    }
+    __syncwarp();
+    if (!has_next) break;
+    cur = nxt;
+    cur_fast = nxt_fast;
+  }
+}
+
+}  // namespace sg

@@ -16,17 +16,11 @@
 // warp and only __syncwarp() is needed.
 #pragma once
 #include "common.cuh"
+#include "plans.cuh"
 #include "ct_math.cuh"
 #include "kernel_w32.cuh"   // bfly, bfly_const, dit_stage_const
 
 namespace sg {
-
-struct WregPlan {
-  const float* win;    // [n_fft]
-  const float2* tw2;   // [31][32]  W_{32*2^u}^{32 p + k_a}, row (2^(u-1) - 1 + p)      (any M)
-  const float2* tw3;   // [32][2^R3 - 1][32]  W_{1024*2^u}^{1024 p + 32 q + k_a}        (M = 2048, 4096)
-  const float2* ut;    // [M/2 + 1] W_n^k
-};
 
 constexpr int kWregThreads = 256;
 constexpr int kWregStride = 33;

@@ -1,0 +1,79 @@
+// Device-side plan tables (built once per (n_fft, window) on the host, sgcore.cu build_plan) and the
+// host-callable launchers of each kernel family.  Every family lives in its own translation unit
+// (tu_*.cu) so a change to one kernel rebuilds only that unit.
+#pragma once
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kW32N = 2048;   // the reference's fftSize (UI/player.js:10): the size with dedicated kernels
+constexpr int kW32M = 1024;
+
+struct W32Plan {        // n_fft == 2048 kernels
+  const float* win;    // [2048]
+  const float2* tw2;   // [31][32]: stage u (1..5), p < 2^(u-1): W_{32*2^u}^{32 p + lane}
+  const float2* ut;    // [16][32]: W_2048^{lane + 32 i}
+};
+
+struct WregPlan {       // register family, n_fft = 256 ... 8192
+  const float* win;    // [n_fft]
+  const float2* tw2;   // [31][32]  W_{32*2^u}^{32 p + k_a}, row (2^(u-1) - 1 + p)      (any M)
+  const float2* tw3;   // [32][2^R3 - 1][32]  W_{1024*2^u}^{1024 p + 32 q + k_a}        (M = 2048, 4096)
+  const float2* ut;    // [M/2 + 1] W_n^k
+};
+
+struct SmemPlan {       // generic mixed-radix kernel
+  const float* win;    // [n_fft]
+  const float2* tw;    // [m]      W_m^k
+  const float2* ut;    // [m/2+1]  W_n^k
+  const int* pos;      // [m]      position of Z[k] after the in-place DIF (digit reversal)
+  int m;               // n_fft/2
+  int nstage;
+  int radix[16];
+};
+
+// Launchers: enqueue on `st`, return the cudaError_t of the launch (0 = ok).  `out_kind` is kOut*.
+int launch_w32x2p(int out_kind, int warps, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out,
+                  int sm_count, int device, cudaStream_t st);
+int launch_w32x2(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
+                 int device, cudaStream_t st);
+int launch_w32x2_nw10(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
+                      int device, cudaStream_t st);   // experiment: 10 warps per SM, 200 registers
+int launch_w32(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
+               int device, cudaStream_t st);
+int launch_wreg(int out_kind, int log2m, const FrameGeom& g, const WregPlan& p, const Epilogue& ep, void* out,
+                int sm_count, int device, cudaStream_t st);
+int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
+                int device, cudaStream_t st);
+
+// tu_wreg.cu is compiled once per output kind
+int launch_wreg_out0(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
+int launch_wreg_out1(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
+int launch_wreg_out2(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
+int launch_wreg_out3(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
+
+constexpr int kMaxDevices = 64;
+
+// one cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per kernel per device
+template <auto Kern>
+inline cudaError_t ensure_dynamic_smem(int bytes, int device) {
+  static int granted[kMaxDevices] = {};
+  const int d = (device >= 0 && device < kMaxDevices) ? device : 0;
+  if (granted[d] >= bytes) return cudaSuccess;
+  const cudaError_t rc = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (rc == cudaSuccess) granted[d] = bytes;
+  return rc;
+}
+
+// dispatch a functor template on the output kind
+template <class F>
+inline int dispatch_out(int out_kind, F&& f) {
+  switch (out_kind) {
+    case kOutU8: return f(std::integral_constant<int, kOutU8>{});
+    case kOutF32Db: return f(std::integral_constant<int, kOutF32Db>{});
+    case kOutRgba8: return f(std::integral_constant<int, kOutRgba8>{});
+    default: return f(std::integral_constant<int, kOutF32Mag>{});
+  }
+}
+
+}  // namespace sg

@@ -17,10 +17,7 @@
 #include <vector>
 
 #include "kernel_misc.cuh"
-#include "kernel_smem.cuh"
-#include "kernel_w32.cuh"
-#include "kernel_w32x2.cuh"
-#include "kernel_wreg.cuh"
+#include "plans.cuh"
 
 namespace {
 
@@ -129,6 +126,8 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
   const int m = p.m, n = p.n_fft;
   std::vector<float> win;
   window_table(cfg.window, n, cfg.custom_window, win);
+  // the frame-pair kernel parks its idle prefetch loads on this table: keep 4096 readable floats behind it
+  if (n == sg::kW32N) win.resize(2 * sg::kW32N, 0.f);
   std::vector<float2> tw(m), ut(m / 2 + 1);
   for (int k = 0; k < m; ++k) tw[k] = expi((double)k / m);
   for (int k = 0; k <= m / 2; ++k) ut[k] = expi((double)k / n);
@@ -302,11 +301,6 @@ struct sg_engine {
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
-  bool w32_attr[4] = {false, false, false, false};   // per-device function attributes already set
-  bool x2_attr[4] = {false, false, false, false};
-  bool x2g_attr[4] = {false, false, false, false};
-  bool wreg_attr[13][4] = {};
-  size_t smem_attr[4] = {0, 0, 0, 0};
   const char* last_kernel = "none";
   std::mutex mu;
 
@@ -335,68 +329,40 @@ struct sg_engine {
 
 namespace {
 
-template <int OUT>
-int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg_stft_config& cfg,
-                    const uint32_t* lut, void* out, cudaStream_t st) {
-  using T = typename sg::OutElem<OUT>::type;
+// Picks the kernel family for a launch group and enqueues it (the families live in tu_*.cu).
+int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg_stft_config& cfg, int out_kind,
+                  const uint32_t* lut, void* out, cudaStream_t st) {
   if (g.total_frames <= 0) return SG_OK;
-  // The packed kernel's byte path takes lg2 with subnormal powers flushed to zero (|X|/N < 1e-19, below
+  const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+  const int v = e->kernel_variant;
+  // The packed kernels' byte path takes lg2 with subnormal powers flushed to zero (|X|/N < 1e-19, below
   // -380 dB): exact for any minDecibels above that, otherwise the one-frame kernel is used.
-  const bool x2_ok = !(OUT == sg::kOutU8 || OUT == sg::kOutRgba8) || cfg.min_db >= -300.f;
-  if (pl.n_fft == sg::kW32N && e->kernel_variant == 0 && x2_ok) {
-    // packed two-frames-per-warp kernel (FFMA2), one persistent CTA per SM
+  const bool bytes_out = out_kind == SG_OUT_U8 || out_kind == SG_OUT_RGBA8;
+  const bool x2_ok = !bytes_out || cfg.min_db >= -300.f;
+  int rc;
+  if (pl.n_fft == sg::kW32N && g.hop == 512 && (v == 0 || v == 6) && x2_ok) {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
-    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
-    const long long pairs = (g.total_frames + 1) / 2;
-    const long long ctas_needed = (pairs + sg::kX2Warps - 1) / sg::kX2Warps;
-    const int grid = (int)std::min<long long>(ctas_needed, e->sm_count);
-    auto launch = [&](auto kern, bool& attr_done) -> int {
-      if (!attr_done) {
-        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sg::kX2SmemBytes));
-        attr_done = true;
-      }
-      kern<<<grid, sg::kX2Warps * 32, sg::kX2SmemBytes, st>>>(g, wp, ep, (T*)out);
-      return SG_OK;
-    };
-    if (g.hop == 512) SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 8>, e->x2_attr[OUT]));
-    else SG_TRY(launch(sg::stft_w32x2_kernel<OUT, 0>, e->x2g_attr[OUT]));
+    rc = sg::launch_w32x2p(out_kind, v == 6 ? 8 : 12, g, wp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "warp32x32x2p";
+  } else if (pl.n_fft == sg::kW32N && g.hop == 512 && v == 5 && out_kind == SG_OUT_U8 && x2_ok) {
+    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+    rc = sg::launch_w32x2_nw10(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "warp32x32x2-10w";
+  } else if (pl.n_fft == sg::kW32N && (v == 0 || v == 4) && x2_ok) {
+    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+    rc = sg::launch_w32x2(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32x2";
-  } else if (pl.n_fft == sg::kW32N && e->kernel_variant != 1 && e->kernel_variant != 3) {
-    bool* attr_set = e->w32_attr;
-    if (!attr_set[OUT]) {
-      SG_CUDA(cudaFuncSetAttribute(sg::stft_w32_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   sg::kW32SmemBytes));
-      attr_set[OUT] = true;
-    }
+  } else if (pl.n_fft == sg::kW32N && v != 1 && v != 3) {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
-    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
-    const long long ctas_needed = (g.total_frames + sg::kW32Warps - 1) / sg::kW32Warps;
-    const int grid = (int)std::min<long long>(ctas_needed, 2LL * e->sm_count);
-    sg::stft_w32_kernel<OUT><<<grid, sg::kW32Warps * 32, sg::kW32SmemBytes, st>>>(g, wp, ep, (T*)out);
+    rc = sg::launch_w32(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32";
-  } else if (pl.log2m >= 7 && pl.log2m <= 12 && e->kernel_variant != 1) {
+  } else if (pl.log2m >= 7 && pl.log2m <= 12 && v != 1) {
     const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
-    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
-    auto launch = [&](auto shape_tag) -> int {
-      constexpr int LM = decltype(shape_tag)::value;
-      using S = sg::WregShape<LM>;
-      bool& done = e->wreg_attr[LM][OUT];
-      if (!done) {
-        SG_CUDA(cudaFuncSetAttribute(sg::stft_wreg_kernel<LM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
-        done = true;
-      }
-      const long long groups = (g.total_frames + S::FPC - 1) / S::FPC;
-      const int grid = (int)std::min<long long>(groups, 2LL * e->sm_count);
-      sg::stft_wreg_kernel<LM, OUT><<<grid, sg::kWregThreads, S::kSmemBytes, st>>>(g, wp, ep, (T*)out);
-      return SG_OK;
-    };
-    switch (pl.log2m) {
-      case 7: SG_TRY(launch(std::integral_constant<int, 7>{})); break;
-      case 8: SG_TRY(launch(std::integral_constant<int, 8>{})); break;
-      case 9: SG_TRY(launch(std::integral_constant<int, 9>{})); break;
-      case 10: SG_TRY(launch(std::integral_constant<int, 10>{})); break;
-      case 11: SG_TRY(launch(std::integral_constant<int, 11>{})); break;
-      default: SG_TRY(launch(std::integral_constant<int, 12>{})); break;
+    switch (out_kind) {
+      case SG_OUT_U8: rc = sg::launch_wreg_out0(pl.log2m, g, wp, ep, out, e->sm_count, e->device, st); break;
+      case SG_OUT_F32_DB: rc = sg::launch_wreg_out1(pl.log2m, g, wp, ep, out, e->sm_count, e->device, st); break;
+      case SG_OUT_RGBA8: rc = sg::launch_wreg_out2(pl.log2m, g, wp, ep, out, e->sm_count, e->device, st); break;
+      default: rc = sg::launch_wreg_out3(pl.log2m, g, wp, ep, out, e->sm_count, e->device, st); break;
     }
     e->last_kernel = "wreg";
   } else {
@@ -404,33 +370,12 @@ int launch_frames_t(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const 
     sp.win = pl.win; sp.tw = pl.tw; sp.ut = pl.ut; sp.pos = pl.pos; sp.m = pl.m;
     sp.nstage = (int)pl.radix.size();
     for (int i = 0; i < sp.nstage; ++i) sp.radix[i] = pl.radix[i];
-    const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
-    const size_t smem = sizeof(float2) * pl.m;
-    size_t* attr_smem = e->smem_attr;
-    if (smem > 48 * 1024 && attr_smem[OUT] < smem) {
-      SG_CUDA(cudaFuncSetAttribute(sg::stft_smem_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-      attr_smem[OUT] = smem;
-    }
-    int threads = std::min(1024, std::max(32, ((pl.m / 4 + 31) / 32) * 32));
-    const int per_sm = std::max(1, std::min<int>(2048 / threads, (int)((200 * 1024) / std::max<size_t>(smem, 1024))));
-    const int grid = (int)std::min<long long>(g.total_frames, (long long)e->sm_count * per_sm);
-    sg::stft_smem_kernel<OUT><<<grid, threads, smem, st>>>(g, sp, ep, (T*)out);
+    rc = sg::launch_smem(out_kind, g, sp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "smem";
   }
   e->launches++;
-  SG_CUDA(cudaGetLastError());
+  SG_CUDA((cudaError_t)rc);
   return SG_OK;
-}
-
-int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg_stft_config& cfg, int out_kind,
-                  const uint32_t* lut, void* out, cudaStream_t st) {
-  switch (out_kind) {
-    case SG_OUT_U8: return launch_frames_t<sg::kOutU8>(e, pl, g, cfg, lut, out, st);
-    case SG_OUT_F32_DB: return launch_frames_t<sg::kOutF32Db>(e, pl, g, cfg, lut, out, st);
-    case SG_OUT_RGBA8: return launch_frames_t<sg::kOutRgba8>(e, pl, g, cfg, lut, out, st);
-    default: return launch_frames_t<sg::kOutF32Mag>(e, pl, g, cfg, lut, out, st);
-  }
 }
 
 template <int OUT>
@@ -606,8 +551,10 @@ int sg_engine_device(const sg_engine* e) { return e ? e->device : SG_ERR_INVALID
 int64_t sg_engine_launch_count(const sg_engine* e) { return e ? e->launches : 0; }
 const char* sg_engine_last_kernel(const sg_engine* e) { return e ? e->last_kernel : "none"; }
 int sg_engine_set_kernel_variant(sg_engine* e, int variant) {
-  if (!e || variant < 0 || variant > 3)
-    return fail(SG_ERR_INVALID_ARG, "variant must be 0 (auto), 1 (generic smem), 2 (one frame per warp) or 3 (register family)");
+  if (!e || variant < 0 || variant > 6)
+    return fail(SG_ERR_INVALID_ARG,
+                "variant must be 0 (auto), 1 (generic smem), 2 (one frame per warp), 3 (register family), "
+                "or 4 (TMA-staged pair kernel)");
   e->kernel_variant = variant;
   return SG_OK;
 }

@@ -52,7 +52,7 @@ def golden_cases():
 
 
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["auto", "generic", "w32"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4], ids=["auto", "generic", "w32", "x2tma"])
 def test_golden(engine, case, variant):
     data = np.load(os.path.join(GOLDEN, case["file"]))
     cfg = O.Config(n_fft=case["n_fft"], hop=case["hop"], window=case["window"], output=case["output"],
@@ -87,7 +87,7 @@ def test_config1_chirp_full(engine):
         for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
             cfg = O.Config(window=window, align=align)
             check_all_outputs(engine, x, cfg)
-            assert engine.last_kernel == "warp32x32x2"
+            assert engine.last_kernel == "warp32x32x2p"
     assert engine.spectrogram(x, sg.Options()).shape == (858, 1024)
     assert engine.spectrogram(x, sg.Options(align="analyser")).shape == (861, 1024)
 
