@@ -79,21 +79,29 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// Loop state is kept small (the FFT needs nearly the whole register file): a pair is (clip, t) of frame A.
+// Loop state is kept small (the FFT needs nearly the whole register file): a pair is (clip, t) of frame A plus
+// the running offset of its first sample, advanced incrementally (no 64-bit multiply or divide in the loop).
 struct PairP {
-  long long fa;   // global index of frame A; frame B = fa + 1
-  int clip, t;    // clip and in-clip index of frame A
+  long long fa;    // global index of frame A; frame B = fa + 1
+  long long off;   // (clip * clip_stride + start0 + t * 512): first sample of frame A, relative to g.pcm
+  int clip, t;     // clip and in-clip index of frame A
 };
-
-// both frames inside one clip, no zero fill, 8-byte aligned first sample
-__device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p) {
-  const long long start_a = g.start0 + (long long)p.t * 512;
-  return p.fa + 1 < g.total_frames && p.t + 1 < g.frames_per_clip && start_a >= 0 &&
-         start_a + 512 + kW32N <= g.clip_len &&
-         ((reinterpret_cast<uintptr_t>(g.pcm + p.clip * g.clip_stride + start_a) & 7) == 0);
+struct PairStep {
+  long long d_off, wrap_off;   // offset advance per step, and its correction when t wraps into the next clip
+  int step, step_clip, step_t, fpc;
+  int t_lo, t_hi;              // pairs with t in [t_lo, t_hi] lie wholly inside their clip (no zero fill)
+  unsigned pcm_lo;             // low address bits of g.pcm (alignment test)
+};
+__device__ __forceinline__ PairP pair_advance(const PairP& c, const PairStep& st) {
+  PairP n;
+  n.fa = c.fa + st.step; n.clip = c.clip + st.step_clip; n.t = c.t + st.step_t; n.off = c.off + st.d_off;
+  if (n.t >= st.fpc) { n.t -= st.fpc; ++n.clip; n.off += st.wrap_off; }
+  return n;
 }
-__device__ __forceinline__ const float2* pair_src(const FrameGeom& g, const PairP& p, int lane) {
-  return reinterpret_cast<const float2*>(g.pcm + p.clip * g.clip_stride + g.start0 + (long long)p.t * 512) + lane;
+// both frames inside one clip, no zero fill, first sample aligned to `align` bytes
+__device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p, const PairStep& st, unsigned align = 8) {
+  return p.fa + 1 < g.total_frames && p.t >= st.t_lo && p.t <= st.t_hi &&
+         ((st.pcm_lo + ((unsigned)p.off << 2)) & (align - 1)) == 0;
 }
 
 template <int OUT, int NW>
@@ -124,15 +132,29 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
   }
   __syncthreads();
 
-  const int fpc = (int)g.frames_per_clip;
-  const int step = 2 * gridDim.x * NW;                 // frames between a warp's consecutive pairs
-  const int step_clip = step / fpc, step_t = step - step_clip * fpc;
+  PairStep st;
+  st.fpc = (int)g.frames_per_clip;
+  st.step = 2 * gridDim.x * NW;                        // frames between a warp's consecutive pairs
+  st.step_clip = st.step / st.fpc;
+  st.step_t = st.step - st.step_clip * st.fpc;
+  st.d_off = (long long)st.step_clip * g.clip_stride + (long long)st.step_t * 512;
+  st.wrap_off = g.clip_stride - (long long)st.fpc * 512;
+  st.pcm_lo = (unsigned)reinterpret_cast<uintptr_t>(g.pcm);
+  {
+    const long long lo = g.start0 >= 0 ? 0 : (-g.start0 + 511) / 512;
+    const long long room = g.clip_len - (512 + kW32N) - g.start0;                 // start0 + 512 t <= room
+    const long long hi = room < 0 ? -1 : min((long long)st.fpc - 2, room / 512);
+    st.t_lo = (int)lo;
+    st.t_hi = (int)hi;
+  }
+  const int fpc = st.fpc;
   PairP cur;
   cur.fa = 2 * ((long long)blockIdx.x * NW + warp);
   if (cur.fa >= g.total_frames) return;
   cur.clip = (int)(cur.fa / fpc);
   cur.t = (int)(cur.fa - (long long)cur.clip * fpc);
-  bool cur_fast = pair_is_fast(g, cur);
+  cur.off = cur.clip * g.clip_stride + g.start0 + (long long)cur.t * 512;
+  bool cur_fast = pair_is_fast(g, cur, st);
   const int partner = (32 - lane) & 31;
   const bool lane0 = lane == 0;
 
@@ -141,7 +163,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
   {
     // loads are unconditional (a pair the fast loader cannot express reads the idle table and ignores it):
     // the destination registers are the loop-carried sample registers themselves, nothing waits on a copy
-    const float2* src = cur_fast ? pair_src(g, cur, lane) : idle_src;
+    const float2* src = cur_fast ? reinterpret_cast<const float2*>(g.pcm + cur.off) + lane : idle_src;
     static_for<0, 40>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
   }
 
@@ -198,9 +220,9 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       asm volatile("bar.sync %0, 32;" ::"r"(warp + 1) : "memory");
       const float4* rre = xp + lane;
       const float4* rim = rre + 16 * kXpStride;
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int q0 = bitrev(j, 4);
+      static_for<0, 16>([&](auto qq) {   // ascending q0: registers stored last are overwritten last
+        constexpr int q0 = decltype(qq)::value;
+        constexpr int j = bitrev(q0, 4);
         const float4 vr = rre[j * kXpStride], vi = rim[j * kXpStride];
         a[q0].re = P2(vr.x, vr.y); a[q0 + 16].re = P2(vr.z, vr.w);
         a[q0].im = P2(vi.x, vi.y); a[q0 + 16].im = P2(vi.z, vi.w);
@@ -221,12 +243,10 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
 
     // ---- next pair: geometry now, its 40 loads interleaved with the untangle below (registers free up as the
     //      untangle consumes Z), so HBM/L2 latency hides behind the untangle and the epilogue
-    PairP nxt;
-    nxt.fa = cur.fa + step; nxt.clip = cur.clip + step_clip; nxt.t = cur.t + step_t;
-    if (nxt.t >= fpc) { nxt.t -= fpc; ++nxt.clip; }
+    const PairP nxt = pair_advance(cur, st);
     const bool has_next = nxt.fa < g.total_frames;
-    const bool nxt_fast = has_next && pair_is_fast(g, nxt);
-    const float2* nsrc = nxt_fast ? pair_src(g, nxt, lane) : idle_src;
+    const bool nxt_fast = has_next && pair_is_fast(g, nxt, st);
+    const float2* nsrc = nxt_fast ? reinterpret_cast<const float2*>(g.pcm + nxt.off) + lane : idle_src;
 
     // ---- untangle.  Z[1024 - k] for k = lane + 32 i is the partner lane's a[31 - i] (lane 0: its own a[32 - i]).
     //      First fetch every mirror IN PLACE (a[31 - i] <- partner's a[31 - i]; descending i keeps lane 0's own
@@ -271,12 +291,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     });
     if (nxt_fast && lane0) {
       // ask L2 for the pair after the next one (one bulk prefetch instruction per pair)
-      PairP n2;
-      n2.fa = nxt.fa + step; n2.clip = nxt.clip + step_clip; n2.t = nxt.t + step_t;
-      if (n2.t >= fpc) { n2.t -= fpc; ++n2.clip; }
-      const float2* p2 = pair_src(g, n2, 0);
-      if (n2.fa + 1 < g.total_frames && n2.t + 1 < fpc && ((reinterpret_cast<uintptr_t>(p2) & 15) == 0))
-        prefetch_l2_bulk(p2, (kW32N + 512) * 4);
+      const PairP n2 = pair_advance(nxt, st);
+      if (pair_is_fast(g, n2, st, 16)) prefetch_l2_bulk(g.pcm + n2.off, (kW32N + 512) * 4);
     }
 
     // ---- epilogue

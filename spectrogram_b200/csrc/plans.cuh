@@ -22,6 +22,12 @@ struct WregPlan {       // register family, n_fft = 256 ... 8192
   const float2* ut;    // [M/2 + 1] W_n^k
 };
 
+struct R400Plan {       // n_fft == 400 kernel (M = 200 = 40 x 5)
+  const float* win;    // [400]
+  const float2* tw;    // [5][41]  W_200^{b k1}, row stride 41
+  const float2* ut;    // [200]    W_400^k
+};
+
 struct SmemPlan {       // generic mixed-radix kernel
   const float* win;    // [n_fft]
   const float2* tw;    // [m]      W_m^k
@@ -43,6 +49,8 @@ int launch_w32(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogu
                int device, cudaStream_t st);
 int launch_wreg(int out_kind, int log2m, const FrameGeom& g, const WregPlan& p, const Epilogue& ep, void* out,
                 int sm_count, int device, cudaStream_t st);
+int launch_r400(int out_kind, const FrameGeom& g, const R400Plan& p, const Epilogue& ep, void* out, int sm_count,
+                int device, cudaStream_t st);
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 

@@ -67,9 +67,11 @@ struct Plan {
   float2* w32_tw2 = nullptr;  // lane-major stage 6-10 twiddles (powers of two, 256 <= n_fft <= 8192)
   float2* w32_ut = nullptr;   // only n_fft == 2048
   float2* wreg_tw3 = nullptr; // lane-major stage 11-12 twiddles (n_fft 4096, 8192)
+  float2* r400_tw = nullptr;  // n_fft == 400: W_200^{b k1} [5][41]
+  float2* r400_ut = nullptr;  // n_fft == 400: W_400^k [200]
   int log2m = 0;              // log2(n_fft/2) when n_fft is a power of two, else 0
   void release() {
-    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3);
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(r400_tw); cudaFree(r400_ut);
   }
 };
 
@@ -168,6 +170,14 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
         }
       SG_TRY(upload(&p.wreg_tw3, tw3));
     }
+  }
+  if (n == 400) {
+    std::vector<float2> tw5(5 * 41), ut4(200);
+    for (int b = 0; b < 5; ++b)
+      for (int k1 = 0; k1 < 41; ++k1) tw5[b * 41 + k1] = expi((double)((b * k1) % 200) / 200.0);
+    for (int k = 0; k < 200; ++k) ut4[k] = expi((double)k / 400.0);
+    SG_TRY(upload(&p.r400_tw, tw5));
+    SG_TRY(upload(&p.r400_ut, ut4));
   }
   if (n == sg::kW32N) {
     std::vector<float2> ut32(16 * 32);
@@ -356,6 +366,10 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32";
+  } else if (pl.n_fft == 400 && v != 1) {
+    const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};
+    rc = sg::launch_r400(out_kind, g, rp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "r400";
   } else if (pl.log2m >= 7 && pl.log2m <= 12 && v != 1) {
     const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
     switch (out_kind) {

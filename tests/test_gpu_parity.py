@@ -123,6 +123,27 @@ def test_config4_n400_clips(engine):
     x = (0.1 * rng.standard_normal((16, 16000))).astype(np.float32)
     check_all_outputs(engine, x, O.Config(n_fft=400, hop=160, window=O.WINDOW_HANN))
     assert engine.spectrogram(x, sg.Options(fftSize=400, hop=160)).shape == (16, 98, 200)
+    assert engine.last_kernel == "r400"
+
+
+@pytest.mark.parametrize("hop,align,clip_len,n_clips", [(160, "valid", 16000, 7), (160, "analyser", 4801, 3),
+                                                        (100, "valid", 3333, 5), (77, "analyser", 1000, 2),
+                                                        (400, "valid", 400, 1), (160, "valid", 399, 2)])
+def test_n400_register_kernel_edges(engine, hop, align, clip_len, n_clips):
+    """Ragged clip lengths, odd hops (unaligned frame starts), zero history, fewer frames than a warp holds."""
+    rng = np.random.default_rng(hop + clip_len)
+    x = (0.2 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    al = O.ALIGN_VALID if align == "valid" else O.ALIGN_ANALYSER
+    check_all_outputs(engine, x, O.Config(n_fft=400, hop=hop, window=O.WINDOW_BLACKMAN, align=al))
+    a = engine.spectrogram(x, sg.Options(fftSize=400, hop=hop, align=align, output="mag"))
+    engine.set_kernel_variant(1)
+    try:
+        b = engine.spectrogram(x, sg.Options(fftSize=400, hop=hop, align=align, output="mag"))
+        assert engine.last_kernel in ("smem", "none")
+    finally:
+        engine.set_kernel_variant(0)
+    if a.size:
+        assert_mag_close(a, b.astype(np.float64))
 
 
 def test_config5_streaming_equals_batch(engine):
