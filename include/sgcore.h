@@ -96,7 +96,8 @@ int sg_engine_destroy(sg_engine* e);
 int sg_engine_device(const sg_engine* e);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 int64_t sg_engine_launch_count(const sg_engine* e);
-/* name of the kernel variant the last sg_stft_* call on this engine used ("warp32x32x2", "warp32x32", "smem") */
+/* name of the kernel family the last sg_stft_* call on this engine used
+ * ("warp32x32x2p", "warp32x32x2", "warp32x32", "wreg", "r400", "smem") */
 const char* sg_engine_last_kernel(const sg_engine* e);
 
 /* ------------------------------------------------------------------ batched path ----------- */
@@ -122,9 +123,11 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
                          int64_t clip_stride, const sg_stft_config* cfg, void* out_dev,
                          void* cuda_stream);
 
-/* 0 = automatic kernel selection; 1 = force the generic shared-memory kernel for every shape;
- * 2 = n_fft 2048 on the one-frame-per-warp kernel instead of the packed two-frame kernel
- * (used by the parity tests to exercise every kernel on n_fft = 2048) */
+/* Kernel selection, for the parity tests (every kernel that can serve a shape is checked against the
+ * oracle) and for A/B timing:  0 = automatic;  1 = generic shared-memory kernel for every shape;
+ * 2 = n_fft 2048 on the one-frame-per-warp kernel;  3 = n_fft 2048 on the register family (wreg);
+ * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;  5 = 4 with 10 warps per SM (u8, hop 512);
+ * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM. */
 int sg_engine_set_kernel_variant(sg_engine* e, int variant);
 
 /* page-locked host memory for the caller's input/output arrays: sg_stft_batch and sg_stream_push

@@ -18,20 +18,27 @@ ap.add_argument("variants", nargs="*", type=int, default=[0, 4])
 ap.add_argument("--out", default="u8")
 ap.add_argument("--clips", type=int, default=256)
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--nfft", type=int, default=2048)
+ap.add_argument("--hop", type=int, default=512)
+ap.add_argument("--clip-len", type=int, default=441000)
+ap.add_argument("--window", default="blackman")
 args = ap.parse_args()
 
 eng = sg.Engine(0)
-clip_len = 441000
-opts = sg.Options(output=args.out)
+clip_len = args.clip_len
+opts = sg.Options(fftSize=args.nfft, hop=args.hop, output=args.out, window=args.window)
 fpc = eng.num_frames(opts, clip_len)
 g = torch.Generator(device="cuda").manual_seed(1)
 x = (torch.rand((args.clips, clip_len), device="cuda", generator=g) - 0.5).float()
 x[0] = torch.from_numpy(O.chirp(clip_len, 44100.0, 20.0, 20000.0, 0.5)).cuda()
 dt = torch.uint8 if args.out == "u8" else torch.float32
-out = torch.empty((args.clips, fpc, 1024), dtype=dt, device="cuda")
-ref = O.spectrogram(x[0].cpu().numpy(), O.Config(output=O.OUT_U8 if args.out == "u8" else O.OUT_F32_DB))[0]
+bins = args.nfft // 2
+out = torch.empty((args.clips, fpc, bins), dtype=dt, device="cuda")
+WIN = {"blackman": O.WINDOW_BLACKMAN, "hann": O.WINDOW_HANN, "rect": O.WINDOW_RECT}
+ref = O.spectrogram(x[0].cpu().numpy(), O.Config(n_fft=args.nfft, hop=args.hop, window=WIN[args.window],
+                                                 output=O.OUT_U8 if args.out == "u8" else O.OUT_F32_DB))[0]
 st = torch.cuda.Stream()
-bpf = 2048 + (1024 if args.out == "u8" else 4096)
+bpf = 4 * args.hop + bins * (1 if args.out == "u8" else 4)
 for v in args.variants:
     eng.set_kernel_variant(v)
     def step():
