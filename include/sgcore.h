@@ -80,6 +80,7 @@ typedef struct sg_stft_config {
 typedef struct sg_engine sg_engine;     /* one per CUDA device; owns stream, plans, scratch   */
 typedef struct sg_analyser sg_analyser; /* AnalyserNode-shaped single-stream object           */
 typedef struct sg_stream sg_stream;     /* many concurrent channels, chunked (BASELINE cfg 5) */
+typedef struct sg_ring sg_ring;         /* the reference's 256-row byte texture + its sonogram view */
 
 /* ------------------------------------------------------------------ library ---------------- */
 const char* sg_last_error(void);  /* thread-local, never NULL                                 */
@@ -187,6 +188,27 @@ int sg_stream_reset(sg_stream* s); /* zero history and smoothing state */
  * colour LUT (only when cfg.output == SG_OUT_U8).  Synchronous: returns when both are filled. */
 int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, uint32_t* out_rgba);
 int64_t sg_stream_frames_emitted(const sg_stream* s); /* per channel */
+
+/* ------------------------------------------------------------------ sonogram ring + view --- */
+/* The reference's spectrogram history: a bins x rows ALPHA/UNSIGNED_BYTE texture, one byte row per
+ * frame written at yoffset, then yoffset = (yoffset + 1) % rows (3D/visualizer.js:60, 301-329,
+ * 399-416; rows = 256 there).  Device resident: a streaming consumer appends rows and fetches the
+ * rendered picture (or the raw texture) instead of re-uploading history. */
+int sg_ring_create(sg_engine* e, int bins, int rows, sg_ring** out);
+int sg_ring_destroy(sg_ring* r);
+int sg_ring_reset(sg_ring* r); /* texture cleared to 0, yoffset 0 (initByteBuffer, visualizer.js:317-329) */
+/* texSubImage2D of n_rows consecutive frames (host [n_rows][bins] u8), wrapping at `rows` */
+int sg_ring_append(sg_ring* r, const uint8_t* frames, int n_rows);
+int sg_ring_yoffset(const sg_ring* r);
+/* the whole texture, host [rows][bins], in texture row order */
+int sg_ring_read(sg_ring* r, uint8_t* dst);
+/* Headless restatement of the sonogram view as an RGBA8 image, host [height][width]:
+ * texCoord u = (px+.5)/width, v = (py+.5)/height; s = 256^(u-1) (log-frequency axis,
+ * bin/shaders/sonogram-fragment.shader:16, sonogram-vertex.shader:51); t = v + yoffset/(rows-1)
+ * (fragment:17, visualizer.js:460); a = LINEAR sample, CLAMP_TO_EDGE in s, REPEAT in t
+ * (visualizer.js:312-315); colour HSV(360-360a,1,1) (sonogram-vertex.shader:19-58, per pixel);
+ * fade sqrt(cos((1-v)pi/2)) (fragment:24); out = clamp(0.08 + a*fade*colour), alpha 255. */
+int sg_ring_view(sg_ring* r, int width, int height, uint32_t* rgba_out);
 
 #ifdef __cplusplus
 }

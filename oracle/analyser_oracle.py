@@ -235,6 +235,67 @@ def colormap_lut_u32() -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
+# sonogram ring + view
+# ----------------------------------------------------------------------------
+class Ring:
+    """The reference's history texture: ``bins x rows`` bytes, one row per frame written at ``yoffset``, then
+    ``yoffset = (yoffset + 1) % rows`` (src/javascripts/3D/visualizer.js:60, 301-329, 399-416)."""
+
+    def __init__(self, bins: int, rows: int = 256):
+        self.bins, self.rows = bins, rows
+        self.tex = np.zeros((rows, bins), dtype=np.uint8)     # initByteBuffer clears the texture (:317-329)
+        self.yoffset = 0
+
+    def append(self, frames) -> None:
+        f = np.atleast_2d(np.asarray(frames, dtype=np.uint8))
+        for row in f:                                         # texSubImage2D(0, yoffset, bins, 1) then advance
+            self.tex[self.yoffset] = row
+            self.yoffset = (self.yoffset + 1) % self.rows
+
+
+def sonogram_view(tex: np.ndarray, yoffset: int, width: int, height: int, background: float = 0.08) -> np.ndarray:
+    """Float64 restatement of the sonogram view, uint8 [height, width, 4].  Per pixel (px, py), texCoord
+    u = (px+.5)/width, v = (py+.5)/height:
+      s = 256^(u-1)                        src/bin/shaders/sonogram-fragment.shader:16, sonogram-vertex.shader:51
+      t = v + yoffset/(rows-1)             sonogram-fragment.shader:17, 3D/visualizer.js:460
+      a = LINEAR sample of alpha, CLAMP_TO_EDGE in s, REPEAT in t                 3D/visualizer.js:312-315
+      rgb = HSV(360 - 360 a, 1, 1)         sonogram-vertex.shader:19-58 (per vertex there, per pixel here)
+      fade = sqrt(cos((1-v) pi/2))         sonogram-fragment.shader:24
+      out = clamp(background + a*fade*rgb), alpha 1; 8-bit round to nearest       sonogram-fragment.shader:26
+    """
+    rows, bins = tex.shape
+    u = (np.arange(width) + 0.5) / width
+    v = (np.arange(height) + 0.5) / height
+    s = 256.0 ** (u - 1.0)
+    t = v + yoffset / (rows - 1.0)
+    t = t - np.floor(t)
+    x = s * bins - 0.5
+    y = t * rows - 0.5
+    x0f, y0f = np.floor(x), np.floor(y)
+    fx, fy = x - x0f, y - y0f
+    x0 = np.clip(x0f.astype(np.int64), 0, bins - 1)
+    x1 = np.clip(x0f.astype(np.int64) + 1, 0, bins - 1)
+    y0 = np.mod(y0f.astype(np.int64), rows)
+    y1 = np.mod(y0 + 1, rows)
+    tx = tex.astype(np.float64)
+    top = tx[y0][:, x0] * (1 - fx)[None, :] + tx[y0][:, x1] * fx[None, :]
+    bot = tx[y1][:, x0] * (1 - fx)[None, :] + tx[y1][:, x1] * fx[None, :]
+    a = (top * (1 - fy)[:, None] + bot * fy[:, None]) / 255.0
+    hd = (360.0 - 360.0 * a) / 60.0
+    xx = 1.0 - np.abs(np.mod(hd, 2.0) - 1.0)
+    r = np.select([hd < 1, hd < 2, hd < 3, hd < 4, hd < 5, hd < 6], [1.0, xx, 0.0, 0.0, xx, 1.0], 0.0)
+    g = np.select([hd < 1, hd < 2, hd < 3, hd < 4, hd < 5, hd < 6], [xx, 1.0, 1.0, xx, 0.0, 0.0], 0.0)
+    b = np.select([hd < 1, hd < 2, hd < 3, hd < 4, hd < 5, hd < 6], [0.0, 0.0, xx, 1.0, 1.0, xx], 0.0)
+    fade = np.sqrt(np.maximum(np.cos((1.0 - v) * 0.5 * math.pi), 0.0))
+    k = a * fade[:, None]
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    for c, ch in enumerate((r, g, b)):
+        out[..., c] = np.floor(np.clip(background + k * ch, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+    out[..., 3] = 255
+    return out
+
+
+# ----------------------------------------------------------------------------
 # whole path, batched: [clips, clip_len] -> [clips, frames, bins]
 # ----------------------------------------------------------------------------
 def spectrogram(pcm: np.ndarray, cfg: Config, chromium_cast: bool = False):

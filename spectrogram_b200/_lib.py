@@ -89,6 +89,13 @@ SIGNATURES = {
     "sg_stream_reset": (C.c_int, [C.c_void_p]),
     "sg_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sg_stream_frames_emitted": (C.c_int64, [C.c_void_p]),
+    "sg_ring_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sg_ring_destroy": (C.c_int, [C.c_void_p]),
+    "sg_ring_reset": (C.c_int, [C.c_void_p]),
+    "sg_ring_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "sg_ring_yoffset": (C.c_int, [C.c_void_p]),
+    "sg_ring_read": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sg_ring_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

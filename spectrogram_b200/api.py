@@ -297,3 +297,56 @@ class StreamBank:
             self.close()
         except Exception:
             pass
+
+
+class SonogramRing:
+    """``sg_ring``: the reference's spectrogram history -- a ``bins x rows`` byte texture written one row per frame at
+    ``yoffset`` (3D/visualizer.js:60, 301-329, 399-416) -- kept on the device, plus its headless sonogram view
+    (bin/shaders/sonogram-fragment.shader:14-27, sonogram-vertex.shader:19-58)."""
+
+    def __init__(self, bins: int, rows: int = 256, engine: Engine | None = None):
+        self.engine = engine or default_engine(0)
+        self._lib = L.load()
+        self.bins, self.rows = int(bins), int(rows)
+        h = C.c_void_p()
+        L.check(self._lib.sg_ring_create(self.engine.handle, self.bins, self.rows, C.byref(h)))
+        self._h = h
+
+    def append(self, frames) -> None:
+        """texSubImage2D of one or more byte rows ([bins] or [n, bins] uint8) at yoffset, then advance yoffset."""
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        if f.ndim == 1:
+            f = f[None, :]
+        if f.ndim != 2 or f.shape[1] != self.bins:
+            raise TypeError("frames must be [n, bins] uint8")
+        L.check(self._lib.sg_ring_append(self._h, f.ctypes.data, f.shape[0]))
+
+    @property
+    def yoffset(self) -> int:
+        return int(self._lib.sg_ring_yoffset(self._h))
+
+    def texture(self) -> np.ndarray:
+        out = np.empty((self.rows, self.bins), dtype=np.uint8)
+        L.check(self._lib.sg_ring_read(self._h, out.ctypes.data))
+        return out
+
+    def view(self, width: int, height: int, out: np.ndarray | None = None) -> np.ndarray:
+        """RGBA8 image [height, width, 4] of the sonogram view (log-frequency x axis, time along y, edge fade)."""
+        if out is None:
+            out = np.empty((int(height), int(width), 4), dtype=np.uint8)
+        L.check(self._lib.sg_ring_view(self._h, int(width), int(height), out.ctypes.data))
+        return out
+
+    def reset(self) -> None:
+        L.check(self._lib.sg_ring_reset(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sg_ring_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

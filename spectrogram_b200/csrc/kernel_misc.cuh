@@ -127,4 +127,47 @@ __global__ void time_domain_byte_kernel(const float* __restrict__ x, uint8_t* __
   if (i < n) out[i] = (uint8_t)byte_from_scaled(128.f * (x[i] + 1.f));
 }
 
+// ---- sonogram view: the picture the reference draws from its byte texture, headless.
+// ring: [rows][bins] u8, the bins x rows ALPHA texture of 3D/visualizer.js:301-329 written row by row at yoffset
+// (:399-416).  One thread per output pixel (px, py), texCoord u = (px+.5)/W, v = (py+.5)/H:
+//   s = 256^(u-1)                         log-frequency axis, sonogram-fragment.shader:16 / sonogram-vertex.shader:51
+//   t = v + yoffset/(rows-1)              fragment:17 with the uniform of visualizer.js:460
+//   a = LINEAR sample of alpha (byte/255), CLAMP_TO_EDGE in s, REPEAT in t      visualizer.js:312-315
+//   rgb = HSV(360 - 360 a, 1, 1)          sonogram-vertex.shader:19-58 (evaluated per pixel here, per vertex there)
+//   fade = sqrt(cos((1-v) pi/2))          fragment:24
+//   out = clamp(0.08 + a*fade*rgb), alpha 1, 8-bit round-to-nearest            fragment:26, visualizer.js:69
+__global__ void __launch_bounds__(256)
+sonogram_view_kernel(const uint8_t* __restrict__ ring, int bins, int rows, int yoffset, int width, int height,
+                     float background, uint32_t* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)width * height) return;
+  const int py = (int)(idx / width), px = (int)(idx - (long long)py * width);
+  const float u = (px + 0.5f) / width, v = (py + 0.5f) / height;
+  const float sc = exp2f(8.f * (u - 1.f));                       // 256^(u-1)
+  float tc = v + (float)yoffset / (float)(rows - 1);
+  tc -= floorf(tc);                                              // REPEAT
+  const float x = sc * bins - 0.5f, y = tc * rows - 0.5f;
+  const float xf = floorf(x), yf = floorf(y);
+  const float fx = x - xf, fy = y - yf;
+  const int x0 = min(max((int)xf, 0), bins - 1), x1 = min(max((int)xf + 1, 0), bins - 1);     // CLAMP_TO_EDGE
+  const int y0 = (((int)yf % rows) + rows) % rows, y1 = (y0 + 1) % rows;                      // REPEAT
+  const float a00 = ring[(long long)y0 * bins + x0], a01 = ring[(long long)y0 * bins + x1];
+  const float a10 = ring[(long long)y1 * bins + x0], a11 = ring[(long long)y1 * bins + x1];
+  const float top = fmaf(fx, a01 - a00, a00), bot = fmaf(fx, a11 - a10, a10);
+  const float a = fmaf(fy, bot - top, top) * (1.f / 255.f);
+  // HSV(hue, 1, 1) with the shader's branch ladder (hue/60 == 6, i.e. a == 0, matches no branch: black)
+  const float hd = (360.f - 360.f * a) * (1.f / 60.f);
+  const float xx = 1.f - fabsf(fmodf(hd, 2.f) - 1.f);
+  float r = 0.f, g = 0.f, b = 0.f;
+  if (hd < 1.f) { r = 1.f; g = xx; }
+  else if (hd < 2.f) { r = xx; g = 1.f; }
+  else if (hd < 3.f) { g = 1.f; b = xx; }
+  else if (hd < 4.f) { g = xx; b = 1.f; }
+  else if (hd < 5.f) { r = xx; b = 1.f; }
+  else if (hd < 6.f) { r = 1.f; b = xx; }
+  const float k = a * sqrtf(fmaxf(cospif((1.f - v) * 0.5f), 0.f));
+  auto q = [&](float c) { return (uint32_t)floorf(fminf(fmaxf(fmaf(k, c, background), 0.f), 1.f) * 255.f + 0.5f); };
+  out[idx] = q(r) | (q(g) << 8) | (q(b) << 16) | 0xFF000000u;
+}
+
 }  // namespace sg

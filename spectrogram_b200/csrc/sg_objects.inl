@@ -102,6 +102,13 @@ struct sg_stream {
   int64_t frames_emitted = 0;
 };
 
+struct sg_ring {
+  sg_engine* e = nullptr;
+  int bins = 0, rows = 0, yoffset = 0;
+  DevBuf tex, img;
+  PinBuf h_img, h_rows;
+};
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------
@@ -348,6 +355,110 @@ int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, u
   if (!out_pin) std::memcpy(out, s->h_out.p, n_out * eb);
   if (out_rgba && !rgba_pin) std::memcpy(out_rgba, s->h_rgba.p, n_out * 4);
   s->frames_emitted += frames;
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sonogram ring: the reference's bins x 256 byte texture (3D/visualizer.js:301-329, 399-416) and its view
+// ------------------------------------------------------------------------------------------
+int sg_ring_reset(sg_ring* r) {
+  if (!r) return fail(SG_ERR_INVALID_ARG, "ring is null");
+  std::lock_guard<std::mutex> lock(r->e->mu);
+  SG_CUDA(cudaSetDevice(r->e->device));
+  SG_CUDA(cudaMemsetAsync(r->tex.p, 0, (size_t)r->bins * r->rows, r->e->stream));
+  r->yoffset = 0;
+  return SG_OK;
+}
+
+int sg_ring_create(sg_engine* e, int bins, int rows, sg_ring** out) {
+  if (!e || !out) return fail(SG_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (bins < 1 || bins > 16384) return fail(SG_ERR_INVALID_ARG, "bins must be in [1, 16384]");
+  if (rows < 2 || rows > 65536) return fail(SG_ERR_INVALID_ARG, "rows must be in [2, 65536]");
+  sg_ring* r = new sg_ring();
+  r->e = e; r->bins = bins; r->rows = rows;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(e->mu);
+    cudaSetDevice(e->device);
+    rc = r->tex.reserve((size_t)bins * rows);
+  }
+  if (rc == SG_OK) rc = sg_ring_reset(r);
+  if (rc != SG_OK) { sg_ring_destroy(r); return rc; }
+  *out = r;
+  return SG_OK;
+}
+
+int sg_ring_destroy(sg_ring* r) {
+  if (!r) return SG_OK;
+  {
+    std::lock_guard<std::mutex> lock(r->e->mu);
+    cudaSetDevice(r->e->device);
+    cudaStreamSynchronize(r->e->stream);
+    r->tex.release(); r->img.release(); r->h_img.release(); r->h_rows.release();
+  }
+  delete r;
+  return SG_OK;
+}
+
+int sg_ring_yoffset(const sg_ring* r) { return r ? r->yoffset : SG_ERR_INVALID_ARG; }
+
+int sg_ring_append(sg_ring* r, const uint8_t* frames, int n_rows) {
+  if (!r) return fail(SG_ERR_INVALID_ARG, "ring is null");
+  if (n_rows < 0 || (n_rows > 0 && !frames)) return fail(SG_ERR_INVALID_ARG, "bad rows");
+  if (n_rows == 0) return SG_OK;
+  sg_engine* e = r->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  SG_CUDA(cudaSetDevice(e->device));
+  // only the last `rows` frames can survive in the texture
+  long long skip = n_rows > r->rows ? n_rows - r->rows : 0;
+  int y = (int)((r->yoffset + skip) % r->rows);
+  const uint8_t* src = frames + skip * r->bins;
+  long long left = n_rows - skip;
+  if (!is_pinned(frames)) {
+    SG_TRY(r->h_rows.reserve((size_t)left * r->bins));
+    std::memcpy(r->h_rows.p, src, (size_t)left * r->bins);
+    src = (const uint8_t*)r->h_rows.p;
+  }
+  while (left > 0) {   // at most two spans: up to the end of the texture, then from row 0
+    const long long span = std::min<long long>(left, r->rows - y);
+    SG_CUDA(cudaMemcpyAsync((uint8_t*)r->tex.p + (size_t)y * r->bins, src, (size_t)span * r->bins,
+                            cudaMemcpyHostToDevice, e->stream));
+    src += span * r->bins; left -= span; y = (int)((y + span) % r->rows);
+  }
+  SG_CUDA(cudaStreamSynchronize(e->stream));   // the caller's buffer is free again (texSubImage2D semantics)
+  r->yoffset = (int)((r->yoffset + (long long)n_rows) % r->rows);
+  return SG_OK;
+}
+
+int sg_ring_read(sg_ring* r, uint8_t* dst) {
+  if (!r || !dst) return fail(SG_ERR_INVALID_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(r->e->mu);
+  SG_CUDA(cudaSetDevice(r->e->device));
+  SG_CUDA(cudaMemcpyAsync(dst, r->tex.p, (size_t)r->bins * r->rows, cudaMemcpyDeviceToHost, r->e->stream));
+  SG_CUDA(cudaStreamSynchronize(r->e->stream));
+  return SG_OK;
+}
+
+int sg_ring_view(sg_ring* r, int width, int height, uint32_t* rgba_out) {
+  if (!r || !rgba_out) return fail(SG_ERR_INVALID_ARG, "null argument");
+  if (width < 1 || height < 1 || (long long)width * height > (1LL << 28))
+    return fail(SG_ERR_INVALID_ARG, "image size out of range");
+  sg_engine* e = r->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  SG_CUDA(cudaSetDevice(e->device));
+  const size_t n = (size_t)width * height;
+  SG_TRY(r->img.reserve(n * 4));
+  sg::sonogram_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+      (const uint8_t*)r->tex.p, r->bins, r->rows, r->yoffset, width, height, 0.08f, (uint32_t*)r->img.p);
+  e->launches++;
+  e->last_kernel = "sonogram_view";
+  SG_CUDA(cudaGetLastError());
+  const bool pin = is_pinned(rgba_out);
+  if (!pin) SG_TRY(r->h_img.reserve(n * 4));
+  SG_CUDA(cudaMemcpyAsync(pin ? (void*)rgba_out : r->h_img.p, r->img.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  SG_CUDA(cudaStreamSynchronize(e->stream));
+  if (!pin) std::memcpy(rgba_out, r->h_img.p, n * 4);
   return SG_OK;
 }
 

@@ -152,11 +152,40 @@ class StreamBank {
   }
 }
 
+// The reference's spectrogram history (a bins x 256 byte texture written one row per frame at yoffset,
+// src/javascripts/3D/visualizer.js:60,301-329,399-416) kept on the device, and its sonogram picture
+// (src/bin/shaders/sonogram-fragment.shader:14-27, sonogram-vertex.shader:19-58) rendered headlessly.
+class SonogramRing {
+  constructor(bins, rows, device) {
+    this.bins = bins;
+    this.rows = rows || 256;
+    this._h = guard(native.ringCreate)(engineFor(device || 0), this.bins, this.rows);
+  }
+  // frames: Uint8Array holding one or more byte rows (what getByteFrequencyData filled)
+  append(frames) {
+    guard(native.ringAppend)(this._h, frames, frames.length / this.bins);
+  }
+  get yoffset() {
+    return native.ringYoffset(this._h);
+  }
+  // RGBA8 picture, Uint32Array [height][width] (little-endian R | G<<8 | B<<16 | A<<24)
+  view(width, height, out) {
+    const img = out || new Uint32Array(width * height);
+    guard(native.ringView)(this._h, width, height, img);
+    return img;
+  }
+  close() {
+    if (this._h) native.ringDestroy(this._h);
+    this._h = null;
+  }
+}
+
 module.exports = {
   AnalyserNode,
   createAnalyser: (options) => new AnalyserNode(options),
   spectrogram,
   StreamBank,
+  SonogramRing,
   colormapReference: () => native.colormapReference(),
   deviceCount: () => native.deviceCount(),
 };

@@ -398,6 +398,70 @@ static napi_value js_stream_destroy(napi_env env, napi_callback_info info) {
   return undefined_of(env);
 }
 
+/* ---------------------------------------------------------------- sonogram ring + view */
+/* ringCreate(engine, bins, rows): the reference's bins x 256 byte texture (3D/visualizer.js:301-329) */
+static napi_value js_ring_create(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS], r;
+  void* e;
+  int32_t bins, rows;
+  sg_ring* ring = NULL;
+  int rc;
+  if (get_args(env, info, argv) < 3 || !get_external(env, argv[0], &e)) return type_error(env, "ringCreate(engine, bins, rows)");
+  if (napi_get_value_int32(env, argv[1], &bins) != napi_ok || napi_get_value_int32(env, argv[2], &rows) != napi_ok)
+    return type_error(env, "bins and rows must be integers");
+  rc = sg_ring_create((sg_engine*)e, bins, rows, &ring);
+  if (rc != SG_OK) return throw_status(env, rc);
+  napi_create_external(env, ring, NULL, NULL, &r);
+  return r;
+}
+
+/* ringAppend(ring, frames: Uint8Array, nRows): texSubImage2D at yoffset + advance (visualizer.js:399-416) */
+static napi_value js_ring_append(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void *ring, *frames;
+  size_t n;
+  int32_t n_rows;
+  int rc;
+  if (get_args(env, info, argv) < 3 || !get_external(env, argv[0], &ring)) return type_error(env, "ringAppend(ring, frames, nRows)");
+  if (!get_typed(env, argv[1], napi_uint8_array, &frames, &n)) return type_error(env, "frames must be a Uint8Array");
+  if (napi_get_value_int32(env, argv[2], &n_rows) != napi_ok) return type_error(env, "nRows must be an integer");
+  rc = sg_ring_append((sg_ring*)ring, (const uint8_t*)frames, n_rows);
+  if (rc != SG_OK) return throw_status(env, rc);
+  return undefined_of(env);
+}
+
+static napi_value js_ring_yoffset(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void* ring;
+  if (get_args(env, info, argv) < 1 || !get_external(env, argv[0], &ring)) return type_error(env, "ring expected");
+  return make_int(env, sg_ring_yoffset((sg_ring*)ring));
+}
+
+/* ringView(ring, width, height, out: Uint32Array): the sonogram picture (sonogram-fragment.shader:14-27) */
+static napi_value js_ring_view(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void *ring, *out;
+  size_t n;
+  int32_t w, h;
+  int rc;
+  if (get_args(env, info, argv) < 4 || !get_external(env, argv[0], &ring)) return type_error(env, "ringView(ring, width, height, out)");
+  if (napi_get_value_int32(env, argv[1], &w) != napi_ok || napi_get_value_int32(env, argv[2], &h) != napi_ok)
+    return type_error(env, "width and height must be integers");
+  if (!get_typed(env, argv[3], napi_uint32_array, &out, &n)) return type_error(env, "out must be a Uint32Array");
+  if (w < 1 || h < 1 || n < (size_t)w * (size_t)h) return type_error(env, "out is smaller than width * height");
+  rc = sg_ring_view((sg_ring*)ring, w, h, (uint32_t*)out);
+  if (rc != SG_OK) return throw_status(env, rc);
+  return undefined_of(env);
+}
+
+static napi_value js_ring_destroy(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void* ring;
+  if (get_args(env, info, argv) < 1 || !get_external(env, argv[0], &ring)) return type_error(env, "ring expected");
+  sg_ring_destroy((sg_ring*)ring);
+  return undefined_of(env);
+}
+
 /* ---------------------------------------------------------------- module init */
 static void export_fn(napi_env env, napi_value exports, const char* name, napi_callback cb) {
   napi_value fn;
@@ -426,6 +490,11 @@ napi_value napi_register_module_v1(napi_env env, napi_value exports) {
   export_fn(env, exports, "streamCreate", js_stream_create);
   export_fn(env, exports, "streamPush", js_stream_push);
   export_fn(env, exports, "streamDestroy", js_stream_destroy);
+  export_fn(env, exports, "ringCreate", js_ring_create);
+  export_fn(env, exports, "ringAppend", js_ring_append);
+  export_fn(env, exports, "ringYoffset", js_ring_yoffset);
+  export_fn(env, exports, "ringView", js_ring_view);
+  export_fn(env, exports, "ringDestroy", js_ring_destroy);
   return exports;
 }
 

@@ -32,6 +32,7 @@ def test_addon_exports_only_the_module_entry_point():
     assert not any(n.startswith("sg_") for n in names)       # the C ABI stays in libsgcore.so
     undefined = subprocess.run(["nm", "-D", "--undefined-only", ADDON], capture_output=True, text=True).stdout
     assert "sg_stft_batch" in undefined and "napi_create_function" in undefined
+    assert "sg_ring_view" in undefined and "sg_ring_append" in undefined
 
 
 def test_js_facade_keeps_the_analysernode_surface():
@@ -40,7 +41,8 @@ def test_js_facade_keeps_the_analysernode_surface():
     text = open(os.path.join(ROOT, "spectrogram_b200", "js", "index.js")).read()
     for name in ("get fftSize", "set fftSize", "get frequencyBinCount", "get minDecibels", "set maxDecibels",
                  "set smoothingTimeConstant", "getByteFrequencyData(array)", "getFloatFrequencyData(array)",
-                 "getByteTimeDomainData(array)", "getFloatTimeDomainData(array)", "createAnalyser", "connect(", "IndexSizeError"):
+                 "getByteTimeDomainData(array)", "getFloatTimeDomainData(array)", "createAnalyser", "connect(", "IndexSizeError",
+                 "class SonogramRing", "append(frames)", "view(width, height, out)"):
         assert name in text, name
 
 
