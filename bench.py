@@ -218,6 +218,16 @@ def bind_near_gpu(index: int) -> str:
         return f"unbound ({type(e).__name__})"
 
 
+def fp32_bound(clocks: dict, frames_per_s_per_gpu: float) -> dict:
+    """The kernel's real ceiling: one frame pair costs 2430 FP32-pipe cycles on one of the 4 x 148
+    schedulers (1064 packed FFMA2/FADD2 ops at 2 cycles + 300 scalar), counted from the SASS of
+    stft_w32x2p_kernel and confirmed by tools/microbench/pipe_bench.cu (2.05 cycles per packed op)."""
+    mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    cap = 148 * 4 * mhz * 1e6 / 2430.0 * 2.0
+    return {"cycles_per_frame_pair": 2430, "cap_frames_per_s": cap, "frac_of_cap": frames_per_s_per_gpu / cap,
+            "cap_as_hbm_frac": cap * BYTES_PER_FRAME / 1e9 / 6551.4}
+
+
 def run_gpu(args) -> None:
     import numpy as np
     import torch
@@ -346,6 +356,7 @@ def run_gpu(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_frame": BYTES_PER_FRAME,
                          "frames_per_launch": frames,
+                         "fp32_pipe": fp32_bound(clocks, value / max(world, 1)),
                          "note": "co-bound by the FP32 pipe: 2430 FP32-pipe cycles per frame pair per scheduler cap the kernel at 43% of HBM peak (DESIGN.md)"},
             "cpu_baseline": cpu,
             "parity": parity,

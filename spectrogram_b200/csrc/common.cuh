@@ -56,6 +56,24 @@ __device__ __forceinline__ unsigned byte_from_scaled(float v) {
   return (unsigned)v;               // truncation, as static_cast<unsigned char> in Chromium
 }
 
+// from unnormalised power p = re^2 + im^2  (tau == 0 path: no sqrt needed); the caller has already applied the
+// non-finite rule (kernels that decide it once per frame)
+template <int OUT>
+__device__ __forceinline__ typename OutElem<OUT>::type emit_power_finite(float p, const Epilogue& e) {
+  if constexpr (OUT == kOutF32Mag) {
+    return sqrtf(p) * e.mag_scale;
+  } else {
+    const float l = __log2f(p);
+    if constexpr (OUT == kOutF32Db) {
+      return fmaf(e.db_scale, l, e.db_off);
+    } else {
+      const unsigned b = byte_from_scaled(fmaf(e.byte_a, l, e.byte_b));
+      if constexpr (OUT == kOutU8) return (uint8_t)b;
+      else return __ldg(e.lut + b);
+    }
+  }
+}
+
 // from unnormalised power p = re^2 + im^2  (tau == 0 path: no sqrt needed)
 template <int OUT>
 __device__ __forceinline__ typename OutElem<OUT>::type emit_power(float p, const Epilogue& e) {

@@ -163,6 +163,13 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
 
     // ---- untangle + epilogue: thread t owns k = t + T i (i < 16) and the mirror bins M - k
     auto zat = [&](int k) { return A[(int)(__brev((unsigned)(k >> 5)) >> (32 - R)) * kWregStride + (k & 31)]; };
+    // [SPEC] "non-finite -> 0" decided once per frame: a non-finite sample makes EVERY Z of its frame non-finite
+    // (each output is a sum over all inputs and Inf*0 = NaN), so one Z tells; the per-bin work is one select.
+    bool bad;
+    {
+      const float2 z0 = zat(t);
+      bad = !(fabsf(z0.x) <= 3.4028235e38f) || !(fabsf(z0.y) <= 3.4028235e38f);
+    }
     TO* __restrict__ row = out + fc * (long long)M;
     static_for<0, 16>([&](auto ii) {
       constexpr int i = decltype(ii)::value;
@@ -176,22 +183,22 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
       const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
       const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
       const float yi = fmaf(2.f, ey, -xi);
-      const float pk = fmaf(xr, xr, xi * xi);
-      float pm = fmaf(yr, yr, yi * yi);
+      const float pk = bad ? 0.f : fmaf(xr, xr, xi * xi);
+      float pm = bad ? 0.f : fmaf(yr, yr, yi * yi);
       int mk = M - k;
       if constexpr (i == 0) {
         if (t == 0) {   // the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2]
           const float2 zh = zat(M / 2);
           mk = M / 2;
-          pm = 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
+          pm = bad ? 0.f : 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
         }
       }
       if constexpr (OUT == kOutU8) {
-        sb[k] = emit_power<OUT>(pk, ep);
-        sb[mk] = emit_power<OUT>(pm, ep);
+        sb[k] = emit_power_finite<OUT>(pk, ep);
+        sb[mk] = emit_power_finite<OUT>(pm, ep);
       } else if (live) {
-        row[k] = emit_power<OUT>(pk, ep);
-        row[mk] = emit_power<OUT>(pm, ep);
+        row[k] = emit_power_finite<OUT>(pk, ep);
+        row[mk] = emit_power_finite<OUT>(pm, ep);
       }
     });
     frame_sync();
