@@ -10,7 +10,7 @@
 //   pass 2   thread c takes 8 of the 40 columns k1 and runs the 5-point DFT over b: Z[k1 + 40 k2].  Columns are
 //            dealt in mirror pairs (k1, 40 - k1), so Z[k] and Z[200 - k] always meet in the SAME thread and the
 //            real-input untangle needs no second exchange (thread 4 also owns the self-mirrored columns 0, 20)
-//   epilogue |X|^2 -> dB / byte / colour, stored straight from registers (5 neighbouring bins per frame)
+//   epilogue |X|^2 -> dB / byte / colour, staged per frame in the idle tile, stored as 16-byte coalesced rows
 // Algorithmic bytes per frame: 4*hop + elem*200 (1440 B for float dB at hop 160).
 #pragma once
 #include "common.cuh"
@@ -22,9 +22,13 @@ namespace sg {
 
 constexpr int kR4N = 400, kR4M = 200;
 constexpr int kR4Warps = 8;
-constexpr int kR4TileStride = 41;                         // float2 per (frame, b) row
-constexpr int kR4TileF2 = 30 * kR4TileStride;             // per warp
-constexpr int kR4TableF2 = kR4M + 5 * kR4TileStride + kR4M;   // window pairs + W_200^{b k1} + W_400^k
+constexpr int kR4TileStride = 49;                         // float2 per (frame, b) row: 98 words = 2 mod 32, so the 16 lanes
+                                                          // of a half-warp hit 32 distinct banks writing AND reading
+constexpr int kR4TwStride = 41;                           // W_200^{b k1} rows
+constexpr int kR4TileF2 = 30 * kR4TileStride;             // per warp: 11760 B
+constexpr int kR4TableF2 = (kR4M + 5 * kR4TwStride + kR4M + 1) & ~1;   // window pairs + W_200^{b k1} + W_400^k, 16-byte padded
+constexpr int kR4OutStrideW = 228;                        // 32-bit outputs: words per staged frame row (16-byte aligned)
+constexpr int kR4OutStrideB = 208;                        // u8 outputs: bytes per staged frame row
 constexpr int kR4SmemBytes = (kR4TableF2 + kR4Warps * kR4TileF2) * 8;
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -106,15 +110,15 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
   extern __shared__ float4 smem_raw[];
   float2* s_win = reinterpret_cast<float2*>(smem_raw);      // [200] (w[2m], w[2m+1])
   float2* s_tw = s_win + kR4M;                              // [5][41] W_200^{b k1}
-  float2* s_ut = s_tw + 5 * kR4TileStride;                  // [200]   W_400^k
+  float2* s_ut = s_tw + 5 * kR4TwStride;                  // [200]   W_400^k
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* tile = s_ut + kR4M + warp * kR4TileF2;
+  float2* tile = s_win + kR4TableF2 + warp * kR4TileF2;   // 16-byte aligned (staged rows leave as uint4)
 
   for (int i = threadIdx.x; i < kR4M; i += blockDim.x) {
     s_win[i] = __ldg(reinterpret_cast<const float2*>(pl.win) + i);
     s_ut[i] = __ldg(pl.ut + i);
   }
-  for (int i = threadIdx.x; i < 5 * kR4TileStride; i += blockDim.x) s_tw[i] = __ldg(pl.tw + i);
+  for (int i = threadIdx.x; i < 5 * kR4TwStride; i += blockDim.x) s_tw[i] = __ldg(pl.tw + i);
   __syncthreads();
 
   const bool active = lane < 30;
@@ -124,40 +128,65 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
   const float2* frame_rows = tile + (g6 * 5) * kR4TileStride;
   const bool special = b == 4;                  // owns the self-mirrored columns 0 and 20 as its 4th pair
 
+  // frame index of this lane's slot, advanced incrementally (no 64-bit division in the loop)
   const long long groups = (g.total_frames + 5) / 6;
-  for (long long grp = (long long)blockIdx.x * kR4Warps + warp; grp < groups; grp += (long long)gridDim.x * kR4Warps) {
-    const long long f = grp * 6 + g6;
+  const long long wstep = (long long)gridDim.x * kR4Warps;          // groups between a warp's iterations
+  const long long fstep = 6 * wstep;                                // frames
+  const long long step_clip = fstep / g.frames_per_clip, step_t = fstep - step_clip * g.frames_per_clip;
+  long long grp = (long long)blockIdx.x * kR4Warps + warp;
+  if (grp >= groups) return;
+  long long f = grp * 6 + g6;
+  long long clip = f / g.frames_per_clip, t = f - clip * g.frames_per_clip;
+  float* scratch = reinterpret_cast<float*>(tile) + g6 * kR4N;      // edge frames are assembled here (tile is idle)
+  for (; grp < groups; grp += wstep) {
     const bool live = active && f < g.total_frames;
-    const long long fc = f < g.total_frames ? f : g.total_frames - 1;   // idle slots recompute the last frame
-    const long long clip = fc / g.frames_per_clip, t = fc - clip * g.frames_per_clip;
-    const long long start = g.start0 + t * g.hop;
-    const float* __restrict__ x = g.pcm + clip * g.clip_stride;
-
-    // ---- steps 1-2: time block, window; thread b takes z[b + 5 j]
-    float2 v[40];
-    const bool interior = start >= 0 && start + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
-    if (interior) {
-      const float2* __restrict__ src = reinterpret_cast<const float2*>(x + start) + b;
-      static_for<0, 40>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        const float2 s = __ldg(src + 5 * j), w = s_win[b + 5 * j];
-        v[j] = make_float2(s.x * w.x, s.y * w.y);
-      });
-    } else {
-      static_for<0, 40>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        const long long s0 = start + 2 * (b + 5 * j), s1 = s0 + 1;
-        const float a0 = (s0 >= 0 && s0 < g.clip_len) ? __ldg(x + s0) : 0.f;
-        const float a1 = (s1 >= 0 && s1 < g.clip_len) ? __ldg(x + s1) : 0.f;
-        const float2 w = s_win[b + 5 * j];
-        v[j] = make_float2(a0 * w.x, a1 * w.y);
-      });
+    long long fc = f, cc = clip, tc = t;
+    if (f >= g.total_frames) {                                      // idle slots recompute the last frame
+      fc = g.total_frames - 1;
+      cc = fc / g.frames_per_clip;
+      tc = fc - cc * g.frames_per_clip;
     }
+    const long long start = g.start0 + tc * g.hop;
+    const float* __restrict__ x = g.pcm + cc * g.clip_stride;
+
+    // ---- steps 1-2: time block, window; thread b takes z[b + 5 j].  Interior, 8-byte aligned frames are read
+    //      straight from global memory; the rest (clip edges / zero history, odd hops) are assembled zero-filled
+    //      in shared memory by a short loop, so one unrolled loader serves both.
+    const bool interior = start >= 0 && start + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
+    const float2* src = reinterpret_cast<const float2*>(x + start) + b;
+    if (!interior) {
+#pragma unroll 1
+      for (int i = b; i < kR4N; i += 5) {
+        const long long q = start + i;
+        scratch[i] = (q >= 0 && q < g.clip_len) ? __ldg(x + q) : 0.f;
+      }
+      src = reinterpret_cast<const float2*>(scratch) + b;
+    }
+    if (__any_sync(0xffffffffu, !interior)) __syncwarp();
+    // ask L2 for the next group's samples while this one is transformed (one request per frame slot)
+    if (b == 0 && active) {
+      const long long nf = f + fstep;
+      if (nf < g.total_frames) {
+        long long nt = t + step_t, nc = clip + step_clip;
+        if (nt >= g.frames_per_clip) { nt -= g.frames_per_clip; ++nc; }
+        const long long ns = g.start0 + nt * g.hop;
+        const float* np = g.pcm + nc * g.clip_stride + ns;
+        if (ns >= 0 && ns + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(np) & 15) == 0))
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(np), "r"(kR4N * 4) : "memory");
+      }
+    }
+    float2 v[40];
+    static_for<0, 40>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      const float2 sv = src[5 * j], w = s_win[b + 5 * j];
+      v[j] = make_float2(sv.x * w.x, sv.y * w.y);
+    });
+    if (__any_sync(0xffffffffu, !interior)) __syncwarp();   // scratch is consumed before the tile is written
 
     // ---- pass 1: 40-point FFT over j, then W_200^{b k1}
     fft40(v);
     {
-      const float2* twb = s_tw + b * kR4TileStride;
+      const float2* twb = s_tw + b * kR4TwStride;
       static_for<0, 8>([&](auto qq) {
         constexpr int q1 = decltype(qq)::value;
         static_for<0, 5>([&](auto rr) {
@@ -185,8 +214,12 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
     __syncwarp();   // the tile is free for the next group
 
     // ---- untangle + epilogue.  Column pair (ka, 40 - ka): bin k = ka + 40 k2 meets 200 - k = kb + 40 (4 - k2).
-    T* __restrict__ row = out + fc * (long long)kR4M;
-    auto put = [&](int k, float p) { if (live) row[k] = emit_power<OUT>(p, ep); };
+    // [SPEC] "non-finite -> 0", decided once per frame (a non-finite sample makes every Z of its frame non-finite)
+    const bool bad = !(fabsf(za[0][0].x) <= 3.4028235e38f) || !(fabsf(za[0][0].y) <= 3.4028235e38f);
+    // results are staged per frame in the (now idle) tile and leave as 16-byte coalesced stores: the six frames of
+    // a warp are consecutive rows of `out`
+    T* stage = reinterpret_cast<T*>(tile) + g6 * (sizeof(T) == 1 ? kR4OutStrideB : kR4OutStrideW);
+    auto put = [&](int k, float p) { stage[k] = emit_power_finite<OUT>(bad ? 0.f : p, ep); };
     static_for<0, 4>([&](auto ii) {
       constexpr int i = decltype(ii)::value;
       const int ka = b + 1 + 5 * i;
@@ -217,6 +250,36 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
         }
       }
     });
+    __syncwarp();
+    {
+      const long long f0 = grp * 6;                                     // first frame of this warp's group
+      const int live_frames = (int)min(6LL, g.total_frames - f0);
+      constexpr int kVecPerFrame = kR4M * (int)sizeof(T) / 16;           // 50 (32-bit) or 12.5 -> handled below
+      if constexpr (sizeof(T) == 4) {
+        const uint4* sv = reinterpret_cast<const uint4*>(tile);
+        uint4* dst = reinterpret_cast<uint4*>(out + f0 * (long long)kR4M);
+#pragma unroll
+        for (int r = 0; r < (6 * kVecPerFrame + 31) / 32; ++r) {
+          const int idx = lane + 32 * r;
+          const int fr = (idx * 1311) >> 16;                            // idx / 50
+          if (idx < 6 * kVecPerFrame && fr < live_frames)
+            dst[idx] = sv[fr * (kR4OutStrideW / 4) + (idx - fr * kVecPerFrame)];
+        }
+      } else {
+        // u8: 200 bytes per frame = 25 8-byte words; the group's rows are contiguous and 8-byte aligned
+        const uint2* sv = reinterpret_cast<const uint2*>(tile);
+        uint2* dst = reinterpret_cast<uint2*>(out + f0 * (long long)kR4M);
+#pragma unroll
+        for (int r = 0; r < (6 * 25 + 31) / 32; ++r) {
+          const int idx = lane + 32 * r;
+          const int fr = (idx * 2622) >> 16;                            // idx / 25
+          if (idx < 6 * 25 && fr < live_frames) dst[idx] = sv[fr * (kR4OutStrideB / 8) + (idx - fr * 25)];
+        }
+      }
+    }
+    __syncwarp();   // the stage is read before the next group's edge frames / tile rows overwrite it
+    f += fstep; clip += step_clip; t += step_t;
+    if (t >= g.frames_per_clip) { t -= g.frames_per_clip; ++clip; }
   }
 }
 
