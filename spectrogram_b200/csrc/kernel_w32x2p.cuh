@@ -8,8 +8,8 @@
 //   loader     the 2560 samples a frame pair covers are read straight into registers (40 coalesced
 //              8-byte loads per lane, the two frames share 24 of every 32), issued for the NEXT pair
 //              during the untangle -- as the FFT registers die -- so the HBM/L2 latency hides behind
-//              the untangle and the dB / byte epilogue; one lane also asks L2 for the pair after that
-//              (cp.async.bulk.prefetch.L2).  No shared-memory stage at all.
+//              the untangle and the dB / byte epilogue (an extra L2 bulk prefetch one pair further ahead
+//              measured no gain and was removed).  No shared-memory stage at all.
 //   exchange   the 32x32 transpose keeps two planes (re, im) of (frame A, frame B) pairs with row pairs
 //              interleaved: 64 STS.64 + 32 LDS.128, bank-conflict free both ways, operands already in
 //              the register pairs/quads the packed arithmetic uses (no moves)
@@ -74,9 +74,6 @@ __device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
   float2 v;
   asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // Loop state is kept small (the FFT needs nearly the whole register file): a pair is (clip, t) of frame A plus
@@ -289,12 +286,6 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         });
       }
     });
-    if (nxt_fast && lane0) {
-      // ask L2 for the pair after the next one (one bulk prefetch instruction per pair)
-      const PairP n2 = pair_advance(nxt, st);
-      if (pair_is_fast(g, n2, st, 16)) prefetch_l2_bulk(g.pcm + n2.off, (kW32N + 512) * 4);
-    }
-
     // ---- epilogue
     const bool has_b_out = cur.fa + 1 < g.total_frames;
     T* __restrict__ row_a = out + cur.fa * (long long)kW32M;
