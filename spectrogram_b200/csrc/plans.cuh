@@ -28,6 +28,12 @@ struct R400Plan {       // n_fft == 400 kernel (M = 200 = 40 x 5)
   const float2* ut;    // [200]    W_400^k
 };
 
+struct W16Plan {        // n_fft == 512 kernel (M = 256 = 16 x 16)
+  const float* win;    // [512]
+  const float2* tw;    // [15][16]  row (h - 1 + p), h = 1, 2, 4, 8: W_{32 h}^{16 p + col}
+  const float2* ut;    // [129]     W_512^k
+};
+
 struct SmemPlan {       // generic mixed-radix kernel
   const float* win;    // [n_fft]
   const float2* tw;    // [m]      W_m^k
@@ -51,6 +57,8 @@ int launch_wreg(int out_kind, int log2m, const FrameGeom& g, const WregPlan& p, 
                 int sm_count, int device, cudaStream_t st);
 int launch_r400(int out_kind, const FrameGeom& g, const R400Plan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
+int launch_w16(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
+               int device, cudaStream_t st);
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 

@@ -67,11 +67,12 @@ struct Plan {
   float2* w32_tw2 = nullptr;  // lane-major stage 6-10 twiddles (powers of two, 256 <= n_fft <= 8192)
   float2* w32_ut = nullptr;   // only n_fft == 2048
   float2* wreg_tw3 = nullptr; // lane-major stage 11-12 twiddles (n_fft 4096, 8192)
+  float2* w16_tw = nullptr;   // n_fft == 512: pass-2 twiddles of the 16 x 16 kernel [15][16]
   float2* r400_tw = nullptr;  // n_fft == 400: W_200^{b k1} [5][41]
   float2* r400_ut = nullptr;  // n_fft == 400: W_400^k [200]
   int log2m = 0;              // log2(n_fft/2) when n_fft is a power of two, else 0
   void release() {
-    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(r400_tw); cudaFree(r400_ut);
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(w16_tw); cudaFree(r400_tw); cudaFree(r400_ut);
   }
 };
 
@@ -170,6 +171,14 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
         }
       SG_TRY(upload(&p.wreg_tw3, tw3));
     }
+  }
+  if (n == 512) {
+    std::vector<float2> tw16(15 * 16);
+    for (int half = 1; half <= 8; half *= 2)
+      for (int pp = 0; pp < half; ++pp)
+        for (int col = 0; col < 16; ++col)
+          tw16[(half - 1 + pp) * 16 + col] = expi((double)(16 * pp + col) / (32.0 * half));
+    SG_TRY(upload(&p.w16_tw, tw16));
   }
   if (n == 400) {
     std::vector<float2> tw5(5 * 41), ut4(200);
@@ -370,6 +379,10 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};
     rc = sg::launch_r400(out_kind, g, rp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "r400";
+  } else if (pl.n_fft == 512 && v != 1 && v != 3) {
+    const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
+    rc = sg::launch_w16(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "w16";
   } else if (pl.log2m >= 7 && pl.log2m <= 12 && v != 1) {
     const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
     switch (out_kind) {

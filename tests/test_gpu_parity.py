@@ -52,7 +52,7 @@ def golden_cases():
 
 
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4], ids=["auto", "generic", "w32", "x2tma"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["auto", "generic", "w32", "wreg", "x2tma"])
 def test_golden(engine, case, variant):
     data = np.load(os.path.join(GOLDEN, case["file"]))
     cfg = O.Config(n_fft=case["n_fft"], hop=case["hop"], window=case["window"], output=case["output"],
