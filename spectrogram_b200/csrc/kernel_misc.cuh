@@ -117,8 +117,18 @@ __global__ void lut_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict_
   if (threadIdx.x < 256) s_lut[threadIdx.x] = lut[threadIdx.x];
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = s_lut[in[i]];
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) & 3) | (reinterpret_cast<uintptr_t>(out) & 15)) == 0) {
+    // four pixels per thread: 16-byte stores (the destination may be page-locked host memory: wide PCIe writes)
+    const uchar4* in4 = reinterpret_cast<const uchar4*>(in);
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    for (long long i = first; i < n / 4; i += stride) {
+      const uchar4 b = in4[i];
+      out4[i] = make_uint4(s_lut[b.x], s_lut[b.y], s_lut[b.z], s_lut[b.w]);
+    }
+    return;
+  }
+  for (long long i = first; i < n; i += stride) out[i] = s_lut[in[i]];
 }
 
 // b = (unsigned char) clamp(128 * (x + 1), 0, 255)   [SPEC getByteTimeDomainData]
