@@ -106,101 +106,183 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
     static_for<0, 32>([&](auto kk) { constexpr int k = decltype(kk)::value; A[t * kWregStride + k] = v[k]; });
     frame_sync();
 
-    // ---- pass 2: stages 6 .. 5+R2; sub-FFT c: column k_a, rows bitrev(q)*L2 + hi2'
-    if constexpr (R2 > 0) {
-      const int hi2p = (R > 5) ? (t >> 5) : 0;
-      static_for<0, S::G2>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int ka = (R > 5) ? (t & 31) : (t + T * c);
-        static_for<0, S::S2>([&](auto qq) {
-          constexpr int q = decltype(qq)::value;
-          v[c * S::S2 + q] = A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka];
-        });
-      });
-      static_for<0, S::G2>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int ka = (R > 5) ? (t & 31) : (t + T * c);
-        dit_stages_table<R2, c * S::S2, 32>(v, pl.tw2 + ka);
-      });
-      static_for<0, S::G2>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int ka = (R > 5) ? (t & 31) : (t + T * c);
-        static_for<0, S::S2>([&](auto qq) {
-          constexpr int q = decltype(qq)::value;
-          A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka] = v[c * S::S2 + q];
-        });
-      });
-      frame_sync();
-    }
-
-    // ---- pass 3: stages 11 .. 10+R3; sub-FFT c: column k_a, q = g*G3 + c, rows bitrev5(q)*L2 + bitrev(h)
-    if constexpr (R3 > 0) {
-      const int ka = t & 31, gq = t >> 5;
-      const int brg = (int)(__brev((unsigned)gq) >> (32 - R3));
-      static_for<0, S::G3>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;   // bitrev5(gq*G3 + c) * L2
-        static_for<0, S::S3>([&](auto hh) {
-          constexpr int h = decltype(hh)::value;
-          v[c * S::S3 + h] = A[(row0 + bitrev(h, R3)) * kWregStride + ka];
-        });
-      });
-      static_for<0, S::G3>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int q = gq * S::G3 + c;
-        dit_stages_table<R3, c * S::S3, 32>(v, pl.tw3 + (q * (S::S3 - 1)) * 32 + ka);
-      });
-      static_for<0, S::G3>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;
-        static_for<0, S::S3>([&](auto hh) {
-          constexpr int h = decltype(hh)::value;
-          A[(row0 + bitrev(h, R3)) * kWregStride + ka] = v[c * S::S3 + h];
-        });
-      });
-      frame_sync();
-    }
-
-    // ---- untangle + epilogue: thread t owns k = t + T i (i < 16) and the mirror bins M - k
-    auto zat = [&](int k) { return A[(int)(__brev((unsigned)(k >> 5)) >> (32 - R)) * kWregStride + (k & 31)]; };
-    // [SPEC] "non-finite -> 0" decided once per frame: a non-finite sample makes EVERY Z of its frame non-finite
-    // (each output is a sum over all inputs and Inf*0 = NaN), so one Z tells; the per-bin work is one select.
-    bool bad;
-    {
-      const float2 z0 = zat(t);
-      bad = !(fabsf(z0.x) <= 3.4028235e38f) || !(fabsf(z0.y) <= 3.4028235e38f);
-    }
     TO* __restrict__ row = out + fc * (long long)M;
-    static_for<0, 16>([&](auto ii) {
-      constexpr int i = decltype(ii)::value;
-      const int k = t + T * i;
-      const int km = (M - k) & (M - 1);
-      const float2 zk = zat(k), zm = zat(km);
-      const float2 w = __ldg(pl.ut + k);
-      const float ex = zk.x + zm.x, ey = zk.y - zm.y;       // 2E
-      const float ox = zk.y + zm.y, oy = zm.x - zk.x;       // 2O
-      const float xr = fmaf(ox, w.x, fmaf(-oy, w.y, ex));   // 2X[k]
-      const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
-      const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
-      const float yi = fmaf(2.f, ey, -xi);
-      const float pk = bad ? 0.f : fmaf(xr, xr, xi * xi);
-      float pm = bad ? 0.f : fmaf(yr, yr, yi * yi);
-      int mk = M - k;
-      if constexpr (i == 0) {
-        if (t == 0) {   // the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2]
-          const float2 zh = zat(M / 2);
-          mk = M / 2;
-          pm = bad ? 0.f : 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
+    if constexpr (R >= 2 && R <= 4) {
+      // ---- T <= 16: pass 2 is 32 columns of T-point FFTs, and the mirror of column c is column 32 - c.  Threads
+      //      take the columns in mirror pairs (pair 0 = the self-mirrored columns 0 and 16), so Z[k] and Z[M - k]
+      //      meet in the SAME thread: no write-back of pass 2 and no second read of the tile for the untangle.
+      constexpr int P = 16 / T;                 // column pairs per thread
+      static_for<0, P>([&](auto rr) {
+        constexpr int r = decltype(rr)::value;
+        const int pi = t + T * r;
+        const int ka = pi, kb = (pi == 0) ? 16 : 32 - pi;
+        static_for<0, T>([&](auto qq) {
+          constexpr int q = decltype(qq)::value;
+          v[(2 * r) * T + q] = A[bitrev(q, R) * kWregStride + ka];
+          v[(2 * r + 1) * T + q] = A[bitrev(q, R) * kWregStride + kb];
+        });
+      });
+      static_for<0, P>([&](auto rr) {
+        constexpr int r = decltype(rr)::value;
+        const int pi = t + T * r;
+        const int ka = pi, kb = (pi == 0) ? 16 : 32 - pi;
+        dit_stages_table<R, (2 * r) * T, 32>(v, pl.tw2 + ka);
+        dit_stages_table<R, (2 * r + 1) * T, 32>(v, pl.tw2 + kb);
+      });
+      // now v[(2r)T + q] = Z[ka + 32 q], v[(2r+1)T + q] = Z[kb + 32 q]
+      const bool bad = !(fabsf(v[0].x) <= 3.4028235e38f) || !(fabsf(v[0].y) <= 3.4028235e38f);
+      auto emit2 = [&](int k, int mk, float pk, float pm) {
+        pk = bad ? 0.f : pk;
+        pm = bad ? 0.f : pm;
+        if constexpr (OUT == kOutU8) {
+          sb[k] = emit_power_finite<OUT>(pk, ep);
+          sb[mk] = emit_power_finite<OUT>(pm, ep);
+        } else if (live) {
+          row[k] = emit_power_finite<OUT>(pk, ep);
+          row[mk] = emit_power_finite<OUT>(pm, ep);
         }
+      };
+      auto untangle = [&](float2 zk, float2 zm, int k, float& pk, float& pm) {
+        const float2 w = __ldg(pl.ut + k);
+        const float ex = zk.x + zm.x, ey = zk.y - zm.y;       // 2E
+        const float ox = zk.y + zm.y, oy = zm.x - zk.x;       // 2O
+        const float xr = fmaf(ox, w.x, fmaf(-oy, w.y, ex));   // 2X[k]
+        const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
+        const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
+        const float yi = fmaf(2.f, ey, -xi);
+        pk = fmaf(xr, xr, xi * xi);
+        pm = fmaf(yr, yr, yi * yi);
+      };
+      static_for<0, P>([&](auto rr) {
+        constexpr int r = decltype(rr)::value;
+        constexpr int oa = (2 * r) * T, ob = (2 * r + 1) * T;
+        const int pi = t + T * r;
+        const int ka = pi, kb = (pi == 0) ? 16 : 32 - pi;
+        // Lower halves of both columns lead (k < M/2, inside the W_n^k table); their mirrors are the upper halves:
+        //   general pair: Z[M - (ka + 32 q)] = column kb, element T-1-q, and vice versa
+        //   pair 0:       column 0 mirrors into itself (element T-q), column 16 into itself (element T-1-q)
+        const bool self = (r == 0) && (t == 0);
+        static_for<0, T / 2>([&](auto qq) {
+          constexpr int q = decltype(qq)::value;
+          float2 zma = v[ob + T - 1 - q], zmb = v[oa + T - 1 - q];
+          if constexpr (r == 0) {
+            const float2 sa = v[oa + ((T - q) % T)], sb2 = v[ob + T - 1 - q];
+            zma = self ? sa : zma;
+            zmb = self ? sb2 : zmb;
+          }
+          float pk, pm;
+          const int k1 = ka + 32 * q;
+          untangle(v[oa + q], zma, k1, pk, pm);
+          int mk1 = M - k1;
+          if constexpr (r == 0 && q == 0) {
+            // thread 0: the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2],
+            // element T/2 of column 0
+            const float2 zh = v[oa + T / 2];
+            pm = self ? 4.f * fmaf(zh.x, zh.x, zh.y * zh.y) : pm;
+            mk1 = self ? M / 2 : mk1;
+          }
+          emit2(k1, mk1, pk, pm);
+          const int k2 = kb + 32 * q;
+          untangle(v[ob + q], zmb, k2, pk, pm);
+          emit2(k2, M - k2, pk, pm);
+        });
+      });
+    } else {
+      // ---- pass 2: stages 6 .. 5+R2; sub-FFT c: column k_a, rows bitrev(q)*L2 + hi2'
+      if constexpr (R2 > 0) {
+        const int hi2p = (R > 5) ? (t >> 5) : 0;
+        static_for<0, S::G2>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int ka = (R > 5) ? (t & 31) : (t + T * c);
+          static_for<0, S::S2>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            v[c * S::S2 + q] = A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka];
+          });
+        });
+        static_for<0, S::G2>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int ka = (R > 5) ? (t & 31) : (t + T * c);
+          dit_stages_table<R2, c * S::S2, 32>(v, pl.tw2 + ka);
+        });
+        static_for<0, S::G2>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int ka = (R > 5) ? (t & 31) : (t + T * c);
+          static_for<0, S::S2>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            A[(bitrev(q, R2) * L2 + hi2p) * kWregStride + ka] = v[c * S::S2 + q];
+          });
+        });
+        frame_sync();
       }
-      if constexpr (OUT == kOutU8) {
-        sb[k] = emit_power_finite<OUT>(pk, ep);
-        sb[mk] = emit_power_finite<OUT>(pm, ep);
-      } else if (live) {
-        row[k] = emit_power_finite<OUT>(pk, ep);
-        row[mk] = emit_power_finite<OUT>(pm, ep);
+
+      // ---- pass 3: stages 11 .. 10+R3; sub-FFT c: column k_a, q = g*G3 + c, rows bitrev5(q)*L2 + bitrev(h)
+      if constexpr (R3 > 0) {
+        const int ka = t & 31, gq = t >> 5;
+        const int brg = (int)(__brev((unsigned)gq) >> (32 - R3));
+        static_for<0, S::G3>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;   // bitrev5(gq*G3 + c) * L2
+          static_for<0, S::S3>([&](auto hh) {
+            constexpr int h = decltype(hh)::value;
+            v[c * S::S3 + h] = A[(row0 + bitrev(h, R3)) * kWregStride + ka];
+          });
+        });
+        static_for<0, S::G3>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int q = gq * S::G3 + c;
+          dit_stages_table<R3, c * S::S3, 32>(v, pl.tw3 + (q * (S::S3 - 1)) * 32 + ka);
+        });
+        static_for<0, S::G3>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;
+          static_for<0, S::S3>([&](auto hh) {
+            constexpr int h = decltype(hh)::value;
+            A[(row0 + bitrev(h, R3)) * kWregStride + ka] = v[c * S::S3 + h];
+          });
+        });
+        frame_sync();
       }
-    });
+
+      // ---- untangle + epilogue: thread t owns k = t + T i (i < 16) and the mirror bins M - k
+      auto zat = [&](int k) { return A[(int)(__brev((unsigned)(k >> 5)) >> (32 - R)) * kWregStride + (k & 31)]; };
+      // [SPEC] "non-finite -> 0" decided once per frame: a non-finite sample makes EVERY Z of its frame non-finite
+      // (each output is a sum over all inputs and Inf*0 = NaN), so one Z tells; the per-bin work is one select.
+      bool bad;
+      {
+        const float2 z0 = zat(t);
+        bad = !(fabsf(z0.x) <= 3.4028235e38f) || !(fabsf(z0.y) <= 3.4028235e38f);
+      }
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int k = t + T * i;
+        const int km = (M - k) & (M - 1);
+        const float2 zk = zat(k), zm = zat(km);
+        const float2 w = __ldg(pl.ut + k);
+        const float ex = zk.x + zm.x, ey = zk.y - zm.y;       // 2E
+        const float ox = zk.y + zm.y, oy = zm.x - zk.x;       // 2O
+        const float xr = fmaf(ox, w.x, fmaf(-oy, w.y, ex));   // 2X[k]
+        const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
+        const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
+        const float yi = fmaf(2.f, ey, -xi);
+        const float pk = bad ? 0.f : fmaf(xr, xr, xi * xi);
+        float pm = bad ? 0.f : fmaf(yr, yr, yi * yi);
+        int mk = M - k;
+        if constexpr (i == 0) {
+          if (t == 0) {   // the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2]
+            const float2 zh = zat(M / 2);
+            mk = M / 2;
+            pm = bad ? 0.f : 4.f * fmaf(zh.x, zh.x, zh.y * zh.y);
+          }
+        }
+        if constexpr (OUT == kOutU8) {
+          sb[k] = emit_power_finite<OUT>(pk, ep);
+          sb[mk] = emit_power_finite<OUT>(pm, ep);
+        } else if (live) {
+          row[k] = emit_power_finite<OUT>(pk, ep);
+          row[mk] = emit_power_finite<OUT>(pm, ep);
+        }
+      });
+    }
     frame_sync();
     if constexpr (OUT == kOutU8) {
       if (live) {
