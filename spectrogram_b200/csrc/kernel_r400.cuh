@@ -149,12 +149,34 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
     const long long start = g.start0 + tc * g.hop;
     const float* __restrict__ x = g.pcm + cc * g.clip_stride;
 
-    // ---- steps 1-2: time block, window; thread b takes z[b + 5 j].  Interior, 8-byte aligned frames are read
-    //      straight from global memory; the rest (clip edges / zero history, odd hops) are assembled zero-filled
-    //      in shared memory by a short loop, so one unrolled loader serves both.
+    // ---- steps 1-2: time block, window; thread b takes z[b + 5 j].
+    //   span path   hop 160 and the warp's six frames are consecutive frames of one clip: they cover ONE contiguous
+    //               span of 1200 samples, which the warp reads as 16-byte coalesced loads (ten per lane instead of
+    //               forty 8-byte loads touching six L1 lines each) into the idle tile, padded by 12 floats per hop so
+    //               the six frames' reads fall on different banks
+    //   frame path  interior, 8-byte aligned frames are read straight from global memory
+    //   edge path   clip edges / zero history / odd hops are assembled zero-filled in the idle tile
+    // All three feed the same unrolled loader below.
+    const long long f0 = grp * 6;
+    const long long clip0 = __shfl_sync(0xffffffffu, clip, 0), t00 = __shfl_sync(0xffffffffu, t, 0);
+    const long long start00 = g.start0 + t00 * 160;
+    const float* span_src = g.pcm + clip0 * g.clip_stride + start00;
+    const bool span = g.hop == 160 && f0 + 5 < g.total_frames && t00 + 5 < g.frames_per_clip && start00 >= 0 &&
+                      start00 + 5 * 160 + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(span_src) & 15) == 0);
     const bool interior = start >= 0 && start + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
     const float2* src = reinterpret_cast<const float2*>(x + start) + b;
-    if (!interior) {
+    int padstep = 0;                    // extra float2 per 16 elements of j (the per-hop padding of the span layout)
+    if (span) {
+      const float4* gs = reinterpret_cast<const float4*>(span_src);
+      float4* sd = reinterpret_cast<float4*>(tile);
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const int q = lane + 32 * r;                         // float4 index in the span, 300 in all
+        if (q < 300) sd[q + 3 * ((q * 1639) >> 16)] = __ldg(gs + q);   // + 3 float4 per 40 (one hop)
+      }
+      src = reinterpret_cast<const float2*>(tile) + 86 * g6 + b;       // (160 + 12) / 2 float2 per hop
+      padstep = 6;
+    } else if (!interior) {
 #pragma unroll 1
       for (int i = b; i < kR4N; i += 5) {
         const long long q = start + i;
@@ -162,26 +184,15 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
       }
       src = reinterpret_cast<const float2*>(scratch) + b;
     }
-    if (__any_sync(0xffffffffu, !interior)) __syncwarp();
-    // ask L2 for the next group's samples while this one is transformed (one request per frame slot)
-    if (b == 0 && active) {
-      const long long nf = f + fstep;
-      if (nf < g.total_frames) {
-        long long nt = t + step_t, nc = clip + step_clip;
-        if (nt >= g.frames_per_clip) { nt -= g.frames_per_clip; ++nc; }
-        const long long ns = g.start0 + nt * g.hop;
-        const float* np = g.pcm + nc * g.clip_stride + ns;
-        if (ns >= 0 && ns + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(np) & 15) == 0))
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(np), "r"(kR4N * 4) : "memory");
-      }
-    }
+    const bool staged = span || __any_sync(0xffffffffu, !interior);
+    if (staged) __syncwarp();
     float2 v[40];
     static_for<0, 40>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
-      const float2 sv = src[5 * j], w = s_win[b + 5 * j];
+      const float2 sv = src[5 * j + (j / 16) * padstep], w = s_win[b + 5 * j];
       v[j] = make_float2(sv.x * w.x, sv.y * w.y);
     });
-    if (__any_sync(0xffffffffu, !interior)) __syncwarp();   // scratch is consumed before the tile is written
+    if (staged) __syncwarp();   // the staged samples are consumed before the tile is written
 
     // ---- pass 1: 40-point FFT over j, then W_200^{b k1}
     fft40(v);
