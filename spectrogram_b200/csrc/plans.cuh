@@ -59,6 +59,8 @@ int launch_r400(int out_kind, const FrameGeom& g, const R400Plan& p, const Epilo
                 int device, cudaStream_t st);
 int launch_w16(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
                int device, cudaStream_t st);
+int launch_w16x8(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
+                 int device, cudaStream_t st);   // n_fft 256; W16Plan.tw holds 7 rows
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 

@@ -172,9 +172,10 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
       SG_TRY(upload(&p.wreg_tw3, tw3));
     }
   }
-  if (n == 512) {
-    std::vector<float2> tw16(15 * 16);
-    for (int half = 1; half <= 8; half *= 2)
+  if (n == 512 || n == 256) {
+    const int rows = n == 512 ? 15 : 7;     // pass 2 is a 16- or 8-point DIT: half = 1 .. rows/2 + 1
+    std::vector<float2> tw16(rows * 16);
+    for (int half = 1; half <= (rows + 1) / 2; half *= 2)
       for (int pp = 0; pp < half; ++pp)
         for (int col = 0; col < 16; ++col)
           tw16[(half - 1 + pp) * 16 + col] = expi((double)(16 * pp + col) / (32.0 * half));
@@ -379,6 +380,10 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};
     rc = sg::launch_r400(out_kind, g, rp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "r400";
+  } else if (pl.n_fft == 256 && v != 1 && v != 3) {
+    const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
+    rc = sg::launch_w16x8(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "w16";
   } else if (pl.n_fft == 512 && v != 1 && v != 3) {
     const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
     rc = sg::launch_w16(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
