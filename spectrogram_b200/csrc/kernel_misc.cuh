@@ -60,7 +60,16 @@ scan_chunk_sums_kernel(const float* __restrict__ mags, float* __restrict__ carry
   const float* __restrict__ m = mags + clip * frames * bins + b;
   const double k1 = 1.0 - tau;
   double s = 0.0;
-  for (long long t = t0; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
+  long long t = t0;
+  // the loads do not depend on the recurrence: eight in flight per thread, then eight dependent updates
+  for (; t + 8 <= t1; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = tau * s + k1 * (double)v[u];
+  }
+  for (; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
   carry[idx] = (float)s;
 }
 
@@ -74,11 +83,22 @@ scan_chunk_carry_kernel(float* __restrict__ carry, const float* __restrict__ sta
   const int b = (int)(idx - clip * bins);
   float* __restrict__ c = carry + clip * n_chunks * bins + b;
   double s = (double)state[idx];
-  for (long long j = 0; j < n_chunks; ++j) {
-    const long long len = min((long long)chunk, frames - j * chunk);
+  const double dec = pow(tau, (double)chunk);   // every chunk but the last is full, and the last one's decay is unused
+  long long j = 0;
+  for (; j + 8 <= n_chunks; j += 8) {
+    float local[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) local[u] = c[(j + u) * bins];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      c[(j + u) * bins] = (float)s;
+      s = dec * s + (double)local[u];
+    }
+  }
+  for (; j < n_chunks; ++j) {
     const double local = (double)c[j * bins];
     c[j * bins] = (float)s;
-    s = pow(tau, (double)len) * s + local;
+    s = dec * s + local;
   }
 }
 
@@ -96,7 +116,18 @@ scan_chunk_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::ty
   typename OutElem<OUT>::type* __restrict__ o = out + clip * frames * bins + b;
   const double k1 = 1.0 - tau;
   float s = carry[idx];
-  for (long long t = t0; t < t1; ++t) {
+  long long t = t0;
+  for (; t + 8 <= t1; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s = finite_or_zero((float)(tau * (double)s + k1 * (double)v[u]));
+      o[(t + u) * bins] = emit_mag<OUT>(s, ep);
+    }
+  }
+  for (; t < t1; ++t) {
     s = finite_or_zero((float)(tau * (double)s + k1 * (double)__ldg(m + t * bins)));
     o[t * bins] = emit_mag<OUT>(s, ep);
   }

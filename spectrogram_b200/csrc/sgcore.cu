@@ -417,7 +417,7 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
   const long long n = n_clips * bins;
   if (n <= 0 || frames <= 0) return SG_OK;
   // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run
-  const long long want_threads = 2048LL * e->sm_count / 4;
+  const long long want_threads = 2048LL * e->sm_count / 2;
   if (n < want_threads && frames >= 256) {
     const int chunk = (int)std::max<long long>(32, std::min<long long>(1024, frames * n / want_threads));
     const long long n_chunks = (frames + chunk - 1) / chunk;
