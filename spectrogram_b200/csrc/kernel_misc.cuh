@@ -48,7 +48,7 @@ smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
 // over chunks that turns those into the true state at every chunk start, (C) the chunks re-run in
 // parallel from their true initial state, emitting dB / bytes.  Inputs are finite (the frame kernel
 // maps non-finite magnitudes to 0), so the [SPEC] non-finite rule cannot fire inside the scan.
-// carry: [n_clips][n_chunks][bins] float.
+// carry: [n_clips][bins][n_chunks] float (chunk fastest: the carry pass reads a bin's chunks coalesced).
 __global__ void __launch_bounds__(256)
 scan_chunk_sums_kernel(const float* __restrict__ mags, float* __restrict__ carry, long long n_clips, long long frames,
                        int bins, int chunk, long long n_chunks, double tau) {
@@ -70,35 +70,38 @@ scan_chunk_sums_kernel(const float* __restrict__ mags, float* __restrict__ carry
     for (int u = 0; u < 8; ++u) s = tau * s + k1 * (double)v[u];
   }
   for (; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
-  carry[idx] = (float)s;
+  carry[(clip * bins + b) * n_chunks + j] = (float)s;
 }
 
-// carry[j] <- state at the START of chunk j (in place); state[clip][bin] holds the clip's initial state
+// carry[j] <- state at the START of chunk j (in place); state[clip][bin] holds the clip's initial state.
+// The pass over chunks is the same linear recurrence (s' = dec*s + local) one level up: one warp per (clip, bin)
+// scans 32 chunks at a time with a shuffle prefix scan of decayed sums, so a 45 000-frame clip needs ~20 warp
+// steps instead of ~600 sequential ones.
 __global__ void __launch_bounds__(256)
 scan_chunk_carry_kernel(float* __restrict__ carry, const float* __restrict__ state, long long n_clips, long long frames,
                         int bins, int chunk, long long n_chunks, double tau) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_clips * bins) return;
-  const long long clip = idx / bins;
-  const int b = (int)(idx - clip * bins);
-  float* __restrict__ c = carry + clip * n_chunks * bins + b;
-  double s = (double)state[idx];
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_clips * bins) return;
+  float* __restrict__ c = carry + warp * n_chunks;
   const double dec = pow(tau, (double)chunk);   // every chunk but the last is full, and the last one's decay is unused
-  long long j = 0;
-  for (; j + 8 <= n_chunks; j += 8) {
-    float local[8];
+  double dpow[5];                               // dec^(2^k)
+  dpow[0] = dec;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) local[u] = c[(j + u) * bins];
+  for (int k = 1; k < 5; ++k) dpow[k] = dpow[k - 1] * dpow[k - 1];
+  const double dec_lane = pow(dec, (double)lane), dec32 = dpow[4] * dpow[4];
+  double s = (double)state[warp];               // state at the start of the current 32-chunk segment
+  for (long long j0 = 0; j0 < n_chunks; j0 += 32) {
+    const long long j = j0 + lane;
+    double y = j < n_chunks ? (double)c[j] : 0.0;           // inclusive decayed prefix sum of the locals
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      c[(j + u) * bins] = (float)s;
-      s = dec * s + (double)local[u];
+    for (int k = 0; k < 5; ++k) {
+      const double up = __shfl_up_sync(0xffffffffu, y, 1 << k);
+      if (lane >= (1 << k)) y = fma(dpow[k], up, y);
     }
-  }
-  for (; j < n_chunks; ++j) {
-    const double local = (double)c[j * bins];
-    c[j * bins] = (float)s;
-    s = dec * s + local;
+    const double prev = __shfl_up_sync(0xffffffffu, y, 1);  // sum of the locals before this chunk
+    if (j < n_chunks) c[j] = (float)(fma(dec_lane, s, lane ? prev : 0.0));
+    s = fma(dec32, s, __shfl_sync(0xffffffffu, y, 31));
   }
 }
 
@@ -115,7 +118,7 @@ scan_chunk_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::ty
   const float* __restrict__ m = mags + clip * frames * bins + b;
   typename OutElem<OUT>::type* __restrict__ o = out + clip * frames * bins + b;
   const double k1 = 1.0 - tau;
-  float s = carry[idx];
+  float s = carry[(clip * bins + b) * n_chunks + j];
   long long t = t0;
   for (; t + 8 <= t1; t += 8) {
     float v[8];

@@ -417,7 +417,7 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
   const long long n = n_clips * bins;
   if (n <= 0 || frames <= 0) return SG_OK;
   // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run
-  const long long want_threads = 2048LL * e->sm_count / 2;
+  const long long want_threads = 2048LL * e->sm_count;
   if (n < want_threads && frames >= 256) {
     const int chunk = (int)std::max<long long>(32, std::min<long long>(1024, frames * n / want_threads));
     const long long n_chunks = (frames + chunk - 1) / chunk;
@@ -426,7 +426,7 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
     const long long nt = n * n_chunks;
     sg::scan_chunk_sums_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, carry, n_clips, frames, bins, chunk,
                                                                            n_chunks, tau);
-    sg::scan_chunk_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry, state, n_clips, frames, bins, chunk,
+    sg::scan_chunk_carry_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(carry, state, n_clips, frames, bins, chunk,
                                                                             n_chunks, tau);
     sg::scan_chunk_emit_kernel<OUT><<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, (T*)out, carry, state, n_clips,
                                                                                 frames, bins, chunk, n_chunks, tau, ep);
