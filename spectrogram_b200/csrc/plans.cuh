@@ -34,6 +34,12 @@ struct W16Plan {        // n_fft == 512 kernel (M = 256 = 16 x 16)
   const float2* ut;    // [129]     W_512^k
 };
 
+struct P16Plan {        // n_fft == 1024 frame-pair kernel (M = 512 = 32 x 16)
+  const float* win;    // [1024], padded to 2048 readable floats (idle prefetches park here)
+  const float2* twb;   // [4][32]  W_{32*2^u}^col, u = 1..4
+  const float2* ut;    // [257]    W_1024^k
+};
+
 struct SmemPlan {       // generic mixed-radix kernel
   const float* win;    // [n_fft]
   const float2* tw;    // [m]      W_m^k
@@ -61,6 +67,8 @@ int launch_w16(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogu
                int device, cudaStream_t st);
 int launch_w16x8(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);   // n_fft 256; W16Plan.tw holds 7 rows
+int launch_p16(int out_kind, const FrameGeom& g, const P16Plan& p, const Epilogue& ep, void* out, int sm_count,
+               int device, cudaStream_t st);   // hop 256 or 128 only
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 
