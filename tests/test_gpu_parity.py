@@ -126,6 +126,31 @@ def test_config4_n400_clips(engine):
     assert engine.last_kernel == "r400"
 
 
+@pytest.mark.parametrize("n_fft,hop,kernel", [(1024, 256, "p16"), (1024, 128, "p16"), (512, 160, "w16"), (256, 64, "w16"),
+                                               (2048, 512, "warp32x32x2p")])
+@pytest.mark.parametrize("align,clip_len,n_clips", [("valid", 9000, 5), ("analyser", 4097, 3), ("valid", 2 * 8192 + 2, 1),
+                                                    ("analyser", 40000, 2)])
+def test_dedicated_kernels_at_clip_edges(engine, n_fft, hop, kernel, align, clip_len, n_clips):
+    """Ragged clip lengths (odd frame counts, pairs straddling clips), zero history, unaligned clip starts: the
+    dedicated kernels against the oracle and against the register family / generic kernel on the same input."""
+    rng = np.random.default_rng(n_fft + hop + clip_len)
+    x = (0.2 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    al = O.ALIGN_VALID if align == "valid" else O.ALIGN_ANALYSER
+    check_all_outputs(engine, x, O.Config(n_fft=n_fft, hop=hop, window=O.WINDOW_BLACKMAN, align=al))
+    o = sg.Options(fftSize=n_fft, hop=hop, align=align, output="mag")
+    a = engine.spectrogram(x, o)
+    if a.size and a.shape[1] >= 4:
+        assert engine.last_kernel == kernel
+    for variant in (1, 3):
+        engine.set_kernel_variant(variant)
+        try:
+            b = engine.spectrogram(x, o)
+        finally:
+            engine.set_kernel_variant(0)
+        if a.size:
+            assert_mag_close(a, b.astype(np.float64))
+
+
 @pytest.mark.parametrize("hop,align,clip_len,n_clips", [(160, "valid", 16000, 7), (160, "analyser", 4801, 3),
                                                         (100, "valid", 3333, 5), (77, "analyser", 1000, 2),
                                                         (400, "valid", 400, 1), (160, "valid", 399, 2)])
@@ -163,8 +188,17 @@ def test_config5_streaming_equals_batch(engine):
     assert i == x.shape[1] and bank.frames_emitted == chunks
     got = np.concatenate(rows, axis=1)
     got_rgba = np.concatenate(rgba_rows, axis=1)
-    batch = engine.spectrogram(x, sg.Options(fftSize=1024, hop=128, align="analyser"))
+    # one-frame-per-channel pushes run on the register family; a batch call on the same kernel is bit identical ...
+    engine.set_kernel_variant(3)
+    try:
+        batch = engine.spectrogram(x, sg.Options(fftSize=1024, hop=128, align="analyser"))
+    finally:
+        engine.set_kernel_variant(0)
     assert np.array_equal(got, batch)            # streaming == batch, bit exact
+    # ... and the batch default (the half-warp pair kernel) agrees within one byte level
+    batch_default = engine.spectrogram(x, sg.Options(fftSize=1024, hop=128, align="analyser"))
+    assert engine.last_kernel == "p16"
+    assert_bytes_close(got, batch_default)
     assert np.array_equal(got_rgba, O.colormap_lut()[got])
     ref = O.spectrogram(x, O.Config(n_fft=1024, hop=128, align=O.ALIGN_ANALYSER))
     assert_bytes_close(got, ref)
