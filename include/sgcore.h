@@ -127,8 +127,9 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
 /* Kernel selection, for the parity tests (every kernel that can serve a shape is checked against the
  * oracle) and for A/B timing:  0 = automatic;  1 = generic shared-memory kernel for every shape;
  * 2 = n_fft 2048 on the one-frame-per-warp kernel;  3 = n_fft 2048 on the register family (wreg);
- * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;  5 = 4 with 10 warps per SM (u8, hop 512);
- * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM. */
+ * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;
+ * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM.
+ * 3 also selects the register family for n_fft 256 / 512 / 1024 (which have dedicated kernels by default). */
 int sg_engine_set_kernel_variant(sg_engine* e, int variant);
 
 /* page-locked host memory for the caller's input/output arrays: sg_stft_batch and sg_stream_push

@@ -28,12 +28,7 @@ constexpr int kX2StageFloats = kW32N + 512;           // both frames' samples wh
 constexpr int kX2BytesStage = 2 * kW32M;              // u8 staging: 1024 (A,B) byte pairs
 constexpr int kX2WarpBytes = kX2PlaneF2 * 8 + kX2StageFloats * 4 + kX2BytesStage + 16;   // 20752 B
 constexpr int kX2Warps = 8;
-template <int NW>
-struct X2Shape {
-  static constexpr int kSmemBytes = kW32TableBytes + NW * kX2WarpBytes;   // 8 warps: ~186 KB, 10 warps: ~222 KB
-  static constexpr int kMaxRegs = NW <= 8 ? 255 : (65536 / (NW * 32)) / 8 * 8;
-};
-constexpr int kX2SmemBytes = X2Shape<kX2Warps>::kSmemBytes;
+constexpr int kX2SmemBytes = kW32TableBytes + kX2Warps * kX2WarpBytes;                   // ~186 KB
 
 // ---------------------------------------------------------------- packed-pair arithmetic
 struct P2 {  // (frame A, frame B)
@@ -187,8 +182,8 @@ __device__ __forceinline__ void window_stage1(C2& lo, C2& hi, float2 a0, float2 
 
 // HOPQ > 0: hop == 64*HOPQ, so frame B's element j is the stage element j + HOPQ of the same lane and the
 // two frames share their loads (32 + HOPQ instead of 64 per lane).  HOPQ == 0: any hop.
-template <int OUT, int HOPQ, int NW = kX2Warps>
-__global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(X2Shape<NW>::kMaxRegs)
+template <int OUT, int HOPQ>
+__global__ void __launch_bounds__(kX2Warps * 32, 1)
 stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
   extern __shared__ float4 smem_raw[];
@@ -213,10 +208,10 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
   __syncthreads();
 
   // frame pair (fa, fa+1); (clip, t) advanced incrementally (no 64-bit division in the loop)
-  const long long step = 2LL * gridDim.x * NW;
+  const long long step = 2LL * gridDim.x * kX2Warps;
   const long long step_clip = step / g.frames_per_clip, step_t = step - step_clip * g.frames_per_clip;
   const unsigned span_bytes = (unsigned)(kW32N + g.hop) * 4u;
-  long long fa0 = 2 * ((long long)blockIdx.x * NW + warp);
+  long long fa0 = 2 * ((long long)blockIdx.x * kX2Warps + warp);
   if (fa0 >= g.total_frames) return;
   PairGeom cur = make_pair(g, fa0, fa0 / g.frames_per_clip, fa0 % g.frames_per_clip);
   if (cur.tma && lane == 0) {

@@ -55,8 +55,6 @@ int launch_w32x2p(int out_kind, int warps, const FrameGeom& g, const W32Plan& p,
                   int sm_count, int device, cudaStream_t st);
 int launch_w32x2(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);
-int launch_w32x2_nw10(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
-                      int device, cudaStream_t st);   // experiment: 10 warps per SM, 200 registers
 int launch_w32(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
                int device, cudaStream_t st);
 int launch_wreg(int out_kind, int log2m, const FrameGeom& g, const WregPlan& p, const Epilogue& ep, void* out,

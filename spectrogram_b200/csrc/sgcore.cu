@@ -372,10 +372,6 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2p(out_kind, v == 6 ? 8 : 12, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32x2p";
-  } else if (pl.n_fft == sg::kW32N && g.hop == 512 && v == 5 && out_kind == SG_OUT_U8 && x2_ok) {
-    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
-    rc = sg::launch_w32x2_nw10(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
-    e->last_kernel = "warp32x32x2-10w";
   } else if (pl.n_fft == sg::kW32N && (v == 0 || v == 4) && x2_ok) {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
@@ -597,10 +593,10 @@ int sg_engine_device(const sg_engine* e) { return e ? e->device : SG_ERR_INVALID
 int64_t sg_engine_launch_count(const sg_engine* e) { return e ? e->launches : 0; }
 const char* sg_engine_last_kernel(const sg_engine* e) { return e ? e->last_kernel : "none"; }
 int sg_engine_set_kernel_variant(sg_engine* e, int variant) {
-  if (!e || variant < 0 || variant > 6)
+  if (!e || variant < 0 || variant > 6 || variant == 5)
     return fail(SG_ERR_INVALID_ARG,
                 "variant must be 0 (auto), 1 (generic smem), 2 (one frame per warp), 3 (register family), "
-                "or 4 (TMA-staged pair kernel)");
+                "4 (TMA-staged pair kernel) or 6 (pair kernel, 8 warps)");
   e->kernel_variant = variant;
   return SG_OK;
 }

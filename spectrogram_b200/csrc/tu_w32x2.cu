@@ -3,19 +3,6 @@
 
 namespace sg {
 
-int launch_w32x2_nw10(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
-                      int device, cudaStream_t st) {
-  if (out_kind != kOutU8 || g.hop != 512) return (int)cudaErrorInvalidValue;
-  using T = OutElem<kOutU8>::type;
-  constexpr int NW = 10;
-  const long long pairs = (g.total_frames + 1) / 2;
-  const int grid = (int)std::min<long long>((pairs + NW - 1) / NW, sm_count);
-  const cudaError_t rc = ensure_dynamic_smem<stft_w32x2_kernel<kOutU8, 8, NW>>(X2Shape<NW>::kSmemBytes, device);
-  if (rc != cudaSuccess) return (int)rc;
-  stft_w32x2_kernel<kOutU8, 8, NW><<<grid, NW * 32, X2Shape<NW>::kSmemBytes, st>>>(g, p, ep, (T*)out);
-  return (int)cudaGetLastError();
-}
-
 int launch_w32x2(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st) {
   return dispatch_out(out_kind, [&](auto tag) {
