@@ -23,7 +23,7 @@
 namespace sg {
 
 constexpr int kP16N = 1024, kP16M = 512;
-constexpr int kP16Warps = 8;
+constexpr int kP16Warps = 12;
 constexpr int kP16PairBytes = 2 * 8 * kXpStride * 16;      // re + im planes of one pair: 8448 B
 constexpr int kP16WarpBytes = 2 * kP16PairBytes;           // two pairs per warp
 constexpr int kP16TableBytes = 16 * 16 * 16 + 4 * 32 * 8 + 258 * 8;   // window quads + 4 bases x 32 columns + W_1024^k
@@ -190,15 +190,20 @@ stft_p16_kernel(FrameGeom g, P16Plan pl, Epilogue ep, typename OutElem<OUT>::typ
     // ---- untangle, in-lane: the lower halves of both columns lead (k < 256); their mirrors are the upper halves.
     //      General lane: Z[512 - (ka + 32 q)] = column kb, element 15 - q, and vice versa.
     //      Lane 0: column 0 mirrors into itself (element 16 - q), column 16 into itself (element 15 - q).
+    //      Lane 0's mirrors are first moved to where the general rule looks (in place, descending q keeps every
+    //      source intact until it is read), so the steps below carry no per-step selects or temporaries.
+    static_for<0, 8>([&](auto qq) {
+      constexpr int q = 7 - decltype(qq)::value;
+      const C2 na = a[q ? 16 - q : 0], nb = a[31 - q];
+      a[31 - q].re = P2(c0 ? na.re.v.x : a[31 - q].re.v.x, c0 ? na.re.v.y : a[31 - q].re.v.y);
+      a[31 - q].im = P2(c0 ? na.im.v.x : a[31 - q].im.v.x, c0 ? na.im.v.y : a[31 - q].im.v.y);
+      a[15 - q].re = P2(c0 ? nb.re.v.x : a[15 - q].re.v.x, c0 ? nb.re.v.y : a[15 - q].re.v.y);
+      a[15 - q].im = P2(c0 ? nb.im.v.x : a[15 - q].im.v.x, c0 ? nb.im.v.y : a[15 - q].im.v.y);
+    });
     P2 pk[16], pm[16];
     static_for<0, 8>([&](auto qq) {
       constexpr int q = decltype(qq)::value;
-      const C2 sa = a[(16 - q) % 16], sbv = a[16 + 15 - q], ga = a[16 + 15 - q], gb = a[15 - q];
-      C2 zma, zmb;
-      zma.re = P2(c0 ? sa.re.v.x : ga.re.v.x, c0 ? sa.re.v.y : ga.re.v.y);
-      zma.im = P2(c0 ? sa.im.v.x : ga.im.v.x, c0 ? sa.im.v.y : ga.im.v.y);
-      zmb.re = P2(c0 ? sbv.re.v.x : gb.re.v.x, c0 ? sbv.re.v.y : gb.re.v.y);
-      zmb.im = P2(c0 ? sbv.im.v.x : gb.im.v.x, c0 ? sbv.im.v.y : gb.im.v.y);
+      const C2 zma = a[31 - q], zmb = a[15 - q];
       auto pair = [&](const C2& zk, const C2& zm, int k, P2& opk, P2& opm) {
         const float2 w = s_ut[k];
         const P2 ex = add2(zk.re, zm.re), ey = add2(zk.im, neg(zm.im));      // 2E
