@@ -34,10 +34,10 @@ struct W16Plan {        // n_fft == 512 kernel (M = 256 = 16 x 16)
   const float2* ut;    // [129]     W_512^k
 };
 
-struct P16Plan {        // n_fft == 1024 frame-pair kernel (M = 512 = 32 x 16)
-  const float* win;    // [1024], padded to 2048 readable floats (idle prefetches park here)
-  const float2* twb;   // [4][32]  W_{32*2^u}^col, u = 1..4
-  const float2* ut;    // [257]    W_1024^k
+struct PairPlan {       // frame-pair kernels for n_fft 1024 (L = 16) and 512 (L = 8), M = 32 x L
+  const float* win;    // [n_fft], padded to 2 n_fft readable floats (idle prefetches park here)
+  const float2* twb;   // [log2 L][32]  W_{32*2^u}^col, u = 1..log2 L
+  const float2* ut;    // [M/2 + 1]     W_n^k
 };
 
 struct SmemPlan {       // generic mixed-radix kernel
@@ -65,8 +65,10 @@ int launch_w16(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogu
                int device, cudaStream_t st);
 int launch_w16x8(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);   // n_fft 256; W16Plan.tw holds 7 rows
-int launch_p16(int out_kind, const FrameGeom& g, const P16Plan& p, const Epilogue& ep, void* out, int sm_count,
-               int device, cudaStream_t st);   // hop 256 or 128 only
+// n_fft 1024 at hop 256 / 128, n_fft 512 at hop 160 / 128; false when the shape has no instantiation
+bool pair_kernel_serves(int n_fft, int hop);
+int launch_pair(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
+                int device, cudaStream_t st);
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 

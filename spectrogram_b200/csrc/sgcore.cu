@@ -67,13 +67,13 @@ struct Plan {
   float2* w32_tw2 = nullptr;  // lane-major stage 6-10 twiddles (powers of two, 256 <= n_fft <= 8192)
   float2* w32_ut = nullptr;   // only n_fft == 2048
   float2* wreg_tw3 = nullptr; // lane-major stage 11-12 twiddles (n_fft 4096, 8192)
-  float2* p16_twb = nullptr;  // n_fft == 1024: pass-2 base twiddles of the half-warp pair kernel [4][32]
+  float2* pair_twb = nullptr; // n_fft 1024 / 512: pass-2 base twiddles of the part-warp pair kernels [log2 L][32]
   float2* w16_tw = nullptr;   // n_fft == 512: pass-2 twiddles of the 16 x 16 kernel [15][16]
   float2* r400_tw = nullptr;  // n_fft == 400: W_200^{b k1} [5][41]
   float2* r400_ut = nullptr;  // n_fft == 400: W_400^k [200]
   int log2m = 0;              // log2(n_fft/2) when n_fft is a power of two, else 0
   void release() {
-    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(p16_twb); cudaFree(w16_tw); cudaFree(r400_tw); cudaFree(r400_ut);
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(pair_twb); cudaFree(w16_tw); cudaFree(r400_tw); cudaFree(r400_ut);
   }
 };
 
@@ -132,7 +132,7 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
   window_table(cfg.window, n, cfg.custom_window, win);
   // the frame-pair kernel parks its idle prefetch loads on this table: keep 4096 readable floats behind it
   if (n == sg::kW32N) win.resize(2 * sg::kW32N, 0.f);
-  if (n == 1024) win.resize(2048, 0.f);
+  if (n == 1024 || n == 512) win.resize(2 * n, 0.f);
   std::vector<float2> tw(m), ut(m / 2 + 1);
   for (int k = 0; k < m; ++k) tw[k] = expi((double)k / m);
   for (int k = 0; k <= m / 2; ++k) ut[k] = expi((double)k / n);
@@ -174,11 +174,12 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
       SG_TRY(upload(&p.wreg_tw3, tw3));
     }
   }
-  if (n == 1024) {
-    std::vector<float2> twb(4 * 32);
-    for (int u = 1; u <= 4; ++u)
+  if (n == 1024 || n == 512) {
+    const int log2l = n == 1024 ? 4 : 3;
+    std::vector<float2> twb(log2l * 32);
+    for (int u = 1; u <= log2l; ++u)
       for (int col = 0; col < 32; ++col) twb[(u - 1) * 32 + col] = expi((double)col / (32.0 * (1 << u)));
-    SG_TRY(upload(&p.p16_twb, twb));
+    SG_TRY(upload(&p.pair_twb, twb));
   }
   if (n == 512 || n == 256) {
     const int rows = n == 512 ? 15 : 7;     // pass 2 is a 16- or 8-point DIT: half = 1 .. rows/2 + 1
@@ -384,12 +385,13 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};
     rc = sg::launch_r400(out_kind, g, rp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "r400";
-  } else if (pl.n_fft == 1024 && (g.hop == 256 || g.hop == 128) && v == 0 && x2_ok && g.frames_per_clip >= 4) {
+  } else if (sg::pair_kernel_serves(pl.n_fft, g.hop) && v == 0 && x2_ok && g.frames_per_clip >= 4 &&
+             (pl.n_fft == 1024 || bytes_out)) {   // n_fft 512 float outputs: the 16 x 16 kernel ties and spills nothing
     // (a streaming push has one frame per channel: consecutive frames are different clips and the pair loader
-    // cannot share their samples -- those launches stay on the register family)
-    const sg::P16Plan pp{pl.win, pl.p16_twb, pl.ut};
-    rc = sg::launch_p16(out_kind, g, pp, ep, out, e->sm_count, e->device, st);
-    e->last_kernel = "p16";
+    // cannot share their samples -- those launches stay on the per-frame kernels)
+    const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
+    rc = sg::launch_pair(out_kind, g, pp, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = pl.n_fft == 1024 ? "p16" : "p8";
   } else if (pl.n_fft == 256 && v != 1 && v != 3) {
     const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
     rc = sg::launch_w16x8(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
