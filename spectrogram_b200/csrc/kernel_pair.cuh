@@ -1,4 +1,4 @@
-// Frame-pair kernels for n_fft = 1024 (L = 16 lanes per pair) and n_fft = 512 (L = 8): the n_fft 2048 kernel of
+// Frame-pair kernels for n_fft = 1024 (L = 16 lanes per pair), 512 (L = 8) and 256 (L = 4): the n_fft 2048 kernel of
 // kernel_w32x2p.cuh folded onto part of a warp.
 //
 // n_fft = 64 L, M = 32 L complex points = 32 x L.  A pair of consecutive frames (A, B) is owned by L lanes -- 32/L
@@ -32,8 +32,9 @@ struct PairShape {
   static constexpr int PW = 32 / L;                  // pairs per warp
   static constexpr int NCOL = 32 / L, NP = NCOL / 2; // columns / mirror pairs per lane
   static constexpr int kPlaneUnits = (L / 2) * kXpStride;                       // 16-byte units per plane
-  // pairs that share a half-warp (L = 8) are offset by 16 banks so their 8-byte stores do not collide
-  static constexpr int kPairBytes = 2 * kPlaneUnits * 16 + (L < 16 ? 64 : 0);
+  // pairs that share a half-warp (L = 8: two, L = 4: four) are offset by 16 / 8 banks so their 8-byte stores do
+  // not collide
+  static constexpr int kPairBytes = 2 * kPlaneUnits * 16 + (L == 16 ? 0 : L == 8 ? 64 : 96);
   static constexpr int kWarpBytes = PW * kPairBytes;
   static constexpr int kUtEntries = M / 2 + 2;
   static constexpr int kTableBytes = 16 * L * 16 + LOG2L * 32 * 8 + kUtEntries * 8;   // window quads, bases, W_N^k

@@ -132,7 +132,7 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
   window_table(cfg.window, n, cfg.custom_window, win);
   // the frame-pair kernel parks its idle prefetch loads on this table: keep 4096 readable floats behind it
   if (n == sg::kW32N) win.resize(2 * sg::kW32N, 0.f);
-  if (n == 1024 || n == 512) win.resize(2 * n, 0.f);
+  if (n == 1024 || n == 512 || n == 256) win.resize(2 * n, 0.f);
   std::vector<float2> tw(m), ut(m / 2 + 1);
   for (int k = 0; k < m; ++k) tw[k] = expi((double)k / m);
   for (int k = 0; k <= m / 2; ++k) ut[k] = expi((double)k / n);
@@ -174,8 +174,8 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
       SG_TRY(upload(&p.wreg_tw3, tw3));
     }
   }
-  if (n == 1024 || n == 512) {
-    const int log2l = n == 1024 ? 4 : 3;
+  if (n == 1024 || n == 512 || n == 256) {
+    const int log2l = n == 1024 ? 4 : n == 512 ? 3 : 2;
     std::vector<float2> twb(log2l * 32);
     for (int u = 1; u <= log2l; ++u)
       for (int col = 0; col < 32; ++col) twb[(u - 1) * 32 + col] = expi((double)col / (32.0 * (1 << u)));
@@ -391,7 +391,7 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     // cannot share their samples -- those launches stay on the per-frame kernels)
     const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
     rc = sg::launch_pair(out_kind, g, pp, ep, out, e->sm_count, e->device, st);
-    e->last_kernel = pl.n_fft == 1024 ? "p16" : "p8";
+    e->last_kernel = pl.n_fft == 1024 ? "p16" : pl.n_fft == 512 ? "p8" : "p4";
   } else if (pl.n_fft == 256 && v != 1 && v != 3) {
     const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
     rc = sg::launch_w16x8(out_kind, g, wp, ep, out, e->sm_count, e->device, st);

@@ -4,7 +4,8 @@
 namespace sg {
 
 bool pair_kernel_serves(int n_fft, int hop) {
-  return (n_fft == 1024 && (hop == 256 || hop == 128)) || (n_fft == 512 && (hop == 160 || hop == 128));
+  return (n_fft == 1024 && (hop == 256 || hop == 128)) || (n_fft == 512 && (hop == 160 || hop == 128)) ||
+         (n_fft == 256 && hop == 64);
 }
 
 template <int OUT, int LOG2L, int HOPJ>
@@ -29,6 +30,7 @@ int launch_pair(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilo
       if (g.hop == 256) return launch_one<OUT, 4, 8>(g, p, ep, out, sm_count, device, st);
       return launch_one<OUT, 4, 4>(g, p, ep, out, sm_count, device, st);
     }
+    if (g.n_fft == 256) return launch_one<OUT, 2, 8>(g, p, ep, out, sm_count, device, st);
     if (g.hop == 160) return launch_one<OUT, 3, 10>(g, p, ep, out, sm_count, device, st);
     return launch_one<OUT, 3, 8>(g, p, ep, out, sm_count, device, st);
   });

@@ -126,7 +126,7 @@ def test_config4_n400_clips(engine):
     assert engine.last_kernel == "r400"
 
 
-@pytest.mark.parametrize("n_fft,hop,kernel", [(1024, 256, "p16"), (1024, 128, "p16"), (512, 160, "p8"), (512, 128, "p8"), (512, 100, "w16"), (256, 64, "w16"),
+@pytest.mark.parametrize("n_fft,hop,kernel", [(1024, 256, "p16"), (1024, 128, "p16"), (512, 160, "p8"), (512, 128, "p8"), (512, 100, "w16"), (256, 64, "p4"), (256, 50, "w16"),
                                                (2048, 512, "warp32x32x2p")])
 @pytest.mark.parametrize("align,clip_len,n_clips", [("valid", 9000, 5), ("analyser", 4097, 3), ("valid", 2 * 8192 + 2, 1),
                                                     ("analyser", 40000, 2)])
