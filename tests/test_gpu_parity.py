@@ -461,3 +461,40 @@ def test_properties_at_full_size(engine):
     sl = xd[: 2048 + 63 * 512].cpu().numpy()
     ref = O.spectrogram(sl, O.Config())[0]
     assert_bytes_close(by1[:64].cpu().numpy(), ref)
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_agree_with_the_generic_kernel(engine, seed):
+    """Seeded random (n_fft, hop, clip length, clip count, alignment, output): whatever kernel the dispatcher picks
+    must agree with the generic shared-memory kernel on the same input (and the bytes with the oracle)."""
+    rng = np.random.default_rng(1000 + seed)
+    n_fft = int(rng.choice([256, 400, 512, 1024, 2048, 4096]))
+    hop = int(rng.choice([n_fft // 4, n_fft // 8, 160, 128, 100, n_fft // 2, n_fft]))
+    n_clips = int(rng.integers(1, 6))
+    clip_len = int(rng.integers(n_fft // 2, 12 * n_fft))
+    align = str(rng.choice(["valid", "analyser"]))
+    out = str(rng.choice(["u8", "db", "mag", "rgba"]))
+    x = (0.3 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    o = sg.Options(fftSize=n_fft, hop=hop, align=align, output="mag")
+    a = engine.spectrogram(x, o)
+    engine.set_kernel_variant(1)
+    try:
+        b = engine.spectrogram(x, o)
+    finally:
+        engine.set_kernel_variant(0)
+    assert a.shape == b.shape
+    if a.size:
+        assert_mag_close(a, b.astype(np.float64))
+    if out != "mag":
+        cfg = O.Config(n_fft=n_fft, hop=hop, align=O.ALIGN_VALID if align == "valid" else O.ALIGN_ANALYSER,
+                       output={"u8": O.OUT_U8, "db": O.OUT_F32_DB, "rgba": O.OUT_RGBA8}[out])
+        got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, align=align, output=out))
+        ref_mag = O.spectrogram(x, O.Config(**{**cfg.__dict__, "output": O.OUT_F32_MAG}))
+        if out == "db":
+            assert_db_close(got, ref_mag)
+        else:
+            ref_u8 = O.finish(ref_mag, O.Config(**{**cfg.__dict__, "output": O.OUT_U8}))
+            if out == "u8":
+                assert_bytes_close(got, ref_u8)
+            else:
+                got_u8 = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, align=align, output="u8"))
+                assert np.array_equal(got, O.colormap_lut()[got_u8])
