@@ -498,3 +498,27 @@ def test_random_shapes_agree_with_the_generic_kernel(engine, seed):
             else:
                 got_u8 = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, align=align, output="u8"))
                 assert np.array_equal(got, O.colormap_lut()[got_u8])
+
+@pytest.mark.parametrize("n_fft,hop", [(256, 64), (400, 160), (512, 160), (512, 128), (1024, 256), (1024, 128), (2048, 512),
+                                       (4096, 1024), (600, 150)])
+@pytest.mark.parametrize("bad_value", [np.nan, np.inf, -np.inf])
+def test_non_finite_samples_zero_their_frames_only(engine, n_fft, hop, bad_value):
+    """[SPEC] "if X^[k] is NaN or infinite, set it to 0": a non-finite sample zeroes exactly the frames that contain it
+    (every kernel decides this once per frame) and leaves the neighbours untouched."""
+    rng = np.random.default_rng(7)
+    n_clips, clip_len = 3, 20 * n_fft
+    x = (0.1 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    clean = {out: engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, output=out)) for out in ("u8", "mag", "db")}
+    pos = 7 * n_fft + 3
+    x[1, pos] = bad_value
+    frames = clean["u8"].shape[1]
+    hit = np.array([t * hop <= pos < t * hop + n_fft for t in range(frames)])
+    assert hit.any() and not hit.all()
+    for out in ("u8", "mag", "db"):
+        got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, output=out))
+        assert np.array_equal(got[0], clean[out][0]) and np.array_equal(got[2], clean[out][2])
+        assert np.array_equal(got[1][~hit], clean[out][1][~hit])
+        if out == "db":
+            assert np.all(np.isneginf(got[1][hit]))
+        else:
+            assert not got[1][hit].any()
