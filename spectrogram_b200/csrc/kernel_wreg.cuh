@@ -65,8 +65,11 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
   unsigned char* fbase = reinterpret_cast<unsigned char*>(smem_raw) + fs * S::kFrameBytes;
   float2* A = reinterpret_cast<float2*>(fbase);
   unsigned char* sb = fbase + S::kTileF2 * 8;
-  auto frame_sync = [] {
-    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
+  // a frame's T threads synchronise among themselves only: __syncwarp inside a warp, otherwise a named barrier per
+  // frame slot (the other frames of the CTA keep running)
+  auto frame_sync = [fs] {
+    if constexpr (T <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(fs + 1), "n"(T) : "memory");
   };
   const long long groups = (g.total_frames + S::FPC - 1) / S::FPC;
   for (long long gi = blockIdx.x; gi < groups; gi += gridDim.x) {
