@@ -24,11 +24,11 @@ namespace sg {
 
 constexpr int kX2Stride = 33;                         // float2 per plane row (odd: 64-bit accesses conflict free)
 constexpr int kX2PlaneF2 = 32 * kX2Stride;            // 1056 float2 = 8448 B: exchange plane (re, then im)
-constexpr int kX2StageFloats = kW32N + 512;           // both frames' samples when hop <= 512
+constexpr int kX2StageFloats = kW32N + 1024;          // both frames' samples when hop <= 1024
 constexpr int kX2BytesStage = 2 * kW32M;              // u8 staging: 1024 (A,B) byte pairs
-constexpr int kX2WarpBytes = kX2PlaneF2 * 8 + kX2StageFloats * 4 + kX2BytesStage + 16;   // 20752 B
+constexpr int kX2WarpBytes = kX2PlaneF2 * 8 + kX2StageFloats * 4 + kX2BytesStage + 16;   // 22800 B
 constexpr int kX2Warps = 8;
-constexpr int kX2SmemBytes = kW32TableBytes + kX2Warps * kX2WarpBytes;                   // ~186 KB
+constexpr int kX2SmemBytes = kW32TableBytes + kX2Warps * kX2WarpBytes;                   // ~203 KB
 
 // ---------------------------------------------------------------- packed-pair arithmetic
 struct P2 {  // (frame A, frame B)
@@ -150,7 +150,7 @@ struct PairGeom {
   long long clip_a, ta;    // clip and in-clip index of A
   long long clip_b, tb;
   bool has_b;
-  bool tma;                // both frames inside one clip, 16-byte aligned span, hop % 4 == 0, hop <= 512
+  bool tma;                // both frames inside one clip, 16-byte aligned span, hop % 4 == 0, hop <= 1024
 };
 
 __device__ __forceinline__ PairGeom make_pair(const FrameGeom& g, long long fa, long long clip_a, long long ta) {
@@ -163,7 +163,7 @@ __device__ __forceinline__ PairGeom make_pair(const FrameGeom& g, long long fa, 
     else p.tb = ta + 1;
   }
   const long long start_a = g.start0 + ta * g.hop;
-  p.tma = p.has_b && p.clip_b == clip_a && g.hop <= 512 && (g.hop & 3) == 0 && start_a >= 0 &&
+  p.tma = p.has_b && p.clip_b == clip_a && g.hop <= 1024 && (g.hop & 3) == 0 && start_a >= 0 &&
           start_a + g.hop + kW32N <= g.clip_len &&
           ((reinterpret_cast<uintptr_t>(g.pcm + clip_a * g.clip_stride + start_a) & 15) == 0);
   return p;
