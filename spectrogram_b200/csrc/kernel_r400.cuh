@@ -177,10 +177,17 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
       src = reinterpret_cast<const float2*>(tile) + 86 * g6 + b;       // (160 + 12) / 2 float2 per hop
       padstep = 6;
     } else if (!interior) {
+      if (start >= 0 && start + kR4N <= g.clip_len) {
+        // inside the clip, only misaligned (odd hops): plain copy, eight loads in flight
+        const float* __restrict__ xs = x + start;
+#pragma unroll 8
+        for (int i = b; i < kR4N; i += 5) scratch[i] = __ldg(xs + i);
+      } else {
 #pragma unroll 1
-      for (int i = b; i < kR4N; i += 5) {
-        const long long q = start + i;
-        scratch[i] = (q >= 0 && q < g.clip_len) ? __ldg(x + q) : 0.f;
+        for (int i = b; i < kR4N; i += 5) {
+          const long long q = start + i;
+          scratch[i] = (q >= 0 && q < g.clip_len) ? __ldg(x + q) : 0.f;
+        }
       }
       src = reinterpret_cast<const float2*>(scratch) + b;
     }
