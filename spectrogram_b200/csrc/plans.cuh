@@ -65,10 +65,21 @@ int launch_w16(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogu
                int device, cudaStream_t st);
 int launch_w16x8(int out_kind, const FrameGeom& g, const W16Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);   // n_fft 256; W16Plan.tw holds 7 rows
-// n_fft 1024 at hop 256 / 128, n_fft 512 at hop 160 / 128; false when the shape has no instantiation
-bool pair_kernel_serves(int n_fft, int hop);
-int launch_pair(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
-                int device, cudaStream_t st);
+// part-warp frame-pair kernels (tu_pair.cu, one object per lane-group size): return -1 when the hop has no
+// instantiation (hop must be 2*L*{4, 8, 16} samples, plus hop 160 for n_fft 1024 and 512)
+int launch_pair_l4(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
+                   int device, cudaStream_t st);   // n_fft 1024
+int launch_pair_l3(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
+                   int device, cudaStream_t st);   // n_fft 512
+int launch_pair_l2(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
+                   int device, cudaStream_t st);   // n_fft 256
+inline bool pair_kernel_serves(int n_fft, int hop) {
+  const int l = n_fft == 1024 ? 16 : n_fft == 512 ? 8 : n_fft == 256 ? 4 : 0;
+  if (!l || hop % (2 * l)) return false;
+  const int j = hop / (2 * l);
+  // (n_fft 256 at hop 128 is faster on the 16 x 8 kernel: 3364 M vs 2812 M frames/s)
+  return j == 4 || j == 8 || (j == 16 && l != 4) || (l == 16 && j == 5) || (l == 8 && j == 10);
+}
 int launch_smem(int out_kind, const FrameGeom& g, const SmemPlan& p, const Epilogue& ep, void* out, int sm_count,
                 int device, cudaStream_t st);
 

@@ -392,7 +392,9 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     // (a streaming push has one frame per channel: consecutive frames are different clips and the pair loader
     // cannot share their samples -- those launches stay on the per-frame kernels)
     const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
-    rc = sg::launch_pair(out_kind, g, pp, ep, out, e->sm_count, e->device, st);
+    rc = pl.n_fft == 1024 ? sg::launch_pair_l4(out_kind, g, pp, ep, out, e->sm_count, e->device, st)
+         : pl.n_fft == 512 ? sg::launch_pair_l3(out_kind, g, pp, ep, out, e->sm_count, e->device, st)
+                           : sg::launch_pair_l2(out_kind, g, pp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = pl.n_fft == 1024 ? "p16" : pl.n_fft == 512 ? "p8" : "p4";
   } else if (pl.n_fft == 256 && v != 1 && v != 3) {
     const sg::W16Plan wp{pl.win, pl.w16_tw, pl.ut};
