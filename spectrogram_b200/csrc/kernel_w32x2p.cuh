@@ -101,10 +101,11 @@ __device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p,
          ((st.pcm_lo + ((unsigned)p.off << 2)) & (align - 1)) == 0;
 }
 
-template <int OUT, int NW>
+template <int OUT, int NW, int HOPJ = 8>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
+  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ;
   extern __shared__ float4 smem_raw[];
   float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
@@ -134,13 +135,13 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
   st.step = 2 * gridDim.x * NW;                        // frames between a warp's consecutive pairs
   st.step_clip = st.step / st.fpc;
   st.step_t = st.step - st.step_clip * st.fpc;
-  st.d_off = (long long)st.step_clip * g.clip_stride + (long long)st.step_t * 512;
-  st.wrap_off = g.clip_stride - (long long)st.fpc * 512;
+  st.d_off = (long long)st.step_clip * g.clip_stride + (long long)st.step_t * HOP;
+  st.wrap_off = g.clip_stride - (long long)st.fpc * HOP;
   st.pcm_lo = (unsigned)reinterpret_cast<uintptr_t>(g.pcm);
   {
-    const long long lo = g.start0 >= 0 ? 0 : (-g.start0 + 511) / 512;
-    const long long room = g.clip_len - (512 + kW32N) - g.start0;                 // start0 + 512 t <= room
-    const long long hi = room < 0 ? -1 : min((long long)st.fpc - 2, room / 512);
+    const long long lo = g.start0 >= 0 ? 0 : (-g.start0 + HOP - 1) / HOP;
+    const long long room = g.clip_len - (HOP + kW32N) - g.start0;                 // start0 + HOP t <= room
+    const long long hi = room < 0 ? -1 : min((long long)st.fpc - 2, room / HOP);
     st.t_lo = (int)lo;
     st.t_hi = (int)hi;
   }
@@ -150,18 +151,18 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
   if (cur.fa >= g.total_frames) return;
   cur.clip = (int)(cur.fa / fpc);
   cur.t = (int)(cur.fa - (long long)cur.clip * fpc);
-  cur.off = cur.clip * g.clip_stride + g.start0 + (long long)cur.t * 512;
+  cur.off = cur.clip * g.clip_stride + g.start0 + (long long)cur.t * HOP;
   bool cur_fast = pair_is_fast(g, cur, st);
   const int partner = (32 - lane) & 31;
   const bool lane0 = lane == 0;
 
-  float2 s[40];   // samples of the current pair (fast path): element m = float2 #(lane + 32 m) of the span
+  float2 s[NLOAD];   // samples of the current pair (fast path): element m = float2 #(lane + 32 m) of the span
   const float2* idle_src = reinterpret_cast<const float2*>(pl.win) + lane;   // 4096 readable floats (build_plan)
   {
     // loads are unconditional (a pair the fast loader cannot express reads the idle table and ignores it):
     // the destination registers are the loop-carried sample registers themselves, nothing waits on a copy
     const float2* src = cur_fast ? reinterpret_cast<const float2*>(g.pcm + cur.off) + lane : idle_src;
-    static_for<0, 40>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
+    static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
   }
 
   while (true) {
@@ -172,7 +173,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         constexpr int j = decltype(jj)::value;
         constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
         const float4 w = s_win4[j * 32 + lane];
-        window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + 8], s[j + 24], make_float2(w.x, w.y), make_float2(w.z, w.w));
+        window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
+                      make_float2(w.z, w.w));
       });
     } else {
       // clip edges / zero history / the last frame of a clip paired with the first of the next
@@ -181,7 +183,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       if (has_b) { if (cur.t + 1 == fpc) { ++clip_b; tb = 0; } else ++tb; }
       const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
       const float* __restrict__ xb = g.pcm + clip_b * g.clip_stride;
-      const long long start_a = g.start0 + (long long)cur.t * 512, start_b = g.start0 + (long long)tb * 512;
+      const long long start_a = g.start0 + (long long)cur.t * HOP, start_b = g.start0 + (long long)tb * HOP;
       auto ld = [&](const float* __restrict__ x, long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(x + q) : 0.f; };
       static_for<0, 16>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
@@ -280,7 +282,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       }
       // this step's share of the next pair's loads
       if constexpr (i < kXpLoadSteps) {
-        static_for<(40 * i) / kXpLoadSteps, (40 * (i + 1)) / kXpLoadSteps>([&](auto mm) {
+        static_for<(NLOAD * i) / kXpLoadSteps, (NLOAD * (i + 1)) / kXpLoadSteps>([&](auto mm) {
           constexpr int m = decltype(mm)::value;
           s[m] = ldg_nc_f2(nsrc + 32 * m);
         });

@@ -369,7 +369,7 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
   const bool bytes_out = out_kind == SG_OUT_U8 || out_kind == SG_OUT_RGBA8;
   const bool x2_ok = !bytes_out || cfg.min_db >= -300.f;
   int rc;
-  if (pl.n_fft == sg::kW32N && g.hop == 512 && (v == 0 || v == 6) && x2_ok) {
+  if (pl.n_fft == sg::kW32N && (g.hop == 512 || (v == 0 && g.hop == 256)) && (v == 0 || v == 6) && x2_ok) {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2p(out_kind, v == 6 ? 8 : 12, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32x2p";
