@@ -84,6 +84,15 @@ stft_w16_kernel(FrameGeom g, W16Plan pl, Epilogue ep, typename OutElem<OUT>::typ
         const float2 s = __ldg(src + 16 * j), w = s_win[t + 16 * j];
         v[bitrev(j, 4)] = make_float2(s.x * w.x, s.y * w.y);
       });
+    } else if (start >= 0 && start + kW16N <= g.clip_len) {
+      // inside the clip, only misaligned (odd hops): 4-byte loads, no bounds checks
+      const float* __restrict__ src = x + start + 2 * t;
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float a0 = __ldg(src + 32 * j), a1 = __ldg(src + 32 * j + 1);
+        const float2 w = s_win[t + 16 * j];
+        v[bitrev(j, 4)] = make_float2(a0 * w.x, a1 * w.y);
+      });
     } else {
       static_for<0, 16>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
@@ -230,6 +239,14 @@ stft_w16x8_kernel(FrameGeom g, W16Plan pl, Epilogue ep, typename OutElem<OUT>::t
         constexpr int j = decltype(jj)::value;
         const float2 s = __ldg(src + 8 * j), w = s_win[t + 8 * j];
         v[bitrev(j, 4)] = make_float2(s.x * w.x, s.y * w.y);
+      });
+    } else if (start >= 0 && start + kW8N <= g.clip_len) {
+      const float* __restrict__ src = x + start + 2 * t;     // inside the clip, only misaligned
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float a0 = __ldg(src + 16 * j), a1 = __ldg(src + 16 * j + 1);
+        const float2 w = s_win[t + 8 * j];
+        v[bitrev(j, 4)] = make_float2(a0 * w.x, a1 * w.y);
       });
     } else {
       static_for<0, 16>([&](auto jj) {

@@ -116,6 +116,15 @@ stft_w32_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::typ
         const float2 w = s_win[lane + 32 * j];
         a[bitrev(j, 5)] = make_float2(v.x * w.x, v.y * w.y);
       });
+    } else if (start >= 0 && start + kW32N <= g.clip_len) {
+      // inside the clip, only misaligned (odd hops): 4-byte loads, no bounds checks
+      const float* __restrict__ src = x + start + 2 * lane;
+      static_for<0, 32>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float v0 = __ldg(src + 64 * j), v1 = __ldg(src + 64 * j + 1);
+        const float2 w = s_win[lane + 32 * j];
+        a[bitrev(j, 5)] = make_float2(v0 * w.x, v1 * w.y);
+      });
     } else {
       static_for<0, 32>([&](auto jj) {
         constexpr int j = decltype(jj)::value;

@@ -91,6 +91,15 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
         const float2 s = __ldg(src + T * j), w = __ldg(win2 + t + T * j);
         v[bitrev(j, 5)] = make_float2(s.x * w.x, s.y * w.y);
       });
+    } else if (start >= 0 && start + N <= g.clip_len) {
+      // inside the clip, only misaligned (odd hops): 4-byte loads, no bounds checks
+      const float* __restrict__ src = x + start + 2 * t;
+      static_for<0, 32>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float a0 = __ldg(src + 2 * T * j), a1 = __ldg(src + 2 * T * j + 1);
+        const float2 w = __ldg(win2 + t + T * j);
+        v[bitrev(j, 5)] = make_float2(a0 * w.x, a1 * w.y);
+      });
     } else {
       static_for<0, 32>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
