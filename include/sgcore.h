@@ -190,6 +190,60 @@ int sg_stream_reset(sg_stream* s); /* zero history and smoothing state */
 int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, uint32_t* out_rgba);
 int64_t sg_stream_frames_emitted(const sg_stream* s); /* per channel */
 
+/* ------------------------------------------------------------------ PCM ingestion ---------- */
+/* The step in front of the path: the reference hands an encoded file to the browser,
+ * context.decodeAudioData(request.response, buffer => ...) (util/util.js:9-17), plays the resulting
+ * AudioBuffer through a buffer source (UI/player.js:110-115, 154-170) and the AnalyserNode down-mixes
+ * whatever channels arrive to mono ([SPEC] AnalyserNode: "as if channelCount 1, channelCountMode max,
+ * channelInterpretation speakers").  Built here for uncompressed PCM (RIFF/WAVE or raw interleaved
+ * samples): sample-format conversion and the speakers down-mix run on the GPU, so 16-bit audio crosses
+ * PCIe at 2 bytes per sample.  Compressed formats and sample-rate conversion are NOT built (the browser's
+ * decoder/resampler are implementation-defined; sample_rate is carried through unchanged). */
+typedef enum sg_pcm_format {
+  SG_PCM_U8 = 0,  /* unsigned 8 bit:            (v - 128) / 128                                 */
+  SG_PCM_S16 = 1, /* little-endian signed 16:   v / 32768                                       */
+  SG_PCM_S24 = 2, /* packed 3-byte signed:      v / 8388608                                     */
+  SG_PCM_S32 = 3, /* signed 32:                 (float)v / 2147483648                           */
+  SG_PCM_F32 = 4  /* IEEE float32, taken as is                                                  */
+} sg_pcm_format;
+
+typedef enum sg_pcm_layout {
+  SG_PCM_MONO_MIX = 0, /* one plane: [SPEC] speakers down-mix to mono -- 1ch: x; 2ch: 0.5(L+R);
+                          4ch: 0.25(L+R+SL+SR); 6ch: sqrt(1/2)(L+R) + C + 0.5(SL+SR); any other
+                          count: discrete, i.e. channel 0                                        */
+  SG_PCM_PLANAR = 1    /* `channels` planes (AudioBuffer.getChannelData(c)), analysed independently */
+} sg_pcm_layout;
+
+typedef struct sg_pcm_info {
+  int32_t format;      /* sg_pcm_format                                                          */
+  int32_t channels;    /* 1..32 interleaved channels                                             */
+  int32_t sample_rate; /* Hz, informational                                                      */
+  int64_t frames;      /* sample frames per clip (AudioBuffer.length)                            */
+  int64_t data_offset; /* sg_wav_parse: byte offset of the first sample in the file; the ingest
+                          calls take a pointer to the first sample and ignore this field         */
+} sg_pcm_info;
+
+/* bytes of one sample of `format` (1, 2, 3, 4, 4), 0 for a bad enum */
+int sg_pcm_sample_bytes(int format);
+/* planes the layout produces for `info`: 1 (mono mix) or info->channels (planar) */
+int sg_pcm_num_planes(const sg_pcm_info* info, int layout);
+/* Host-side RIFF/WAVE header walk (fmt + data chunks; PCM, IEEE float and WAVE_FORMAT_EXTENSIBLE).
+ * Fills `out` (frames clipped to what the file actually holds).  No GPU involved. */
+int sg_wav_parse(const void* file_bytes, size_t len, sg_pcm_info* out);
+/* decodeAudioData for uncompressed PCM: n_clips clips of info->frames interleaved sample frames each,
+ * back to back in host memory at `pcm`  ->  out host float32 [n_clips][planes][frames]. */
+int sg_pcm_ingest(sg_engine* e, const void* pcm, int64_t n_clips, const sg_pcm_info* info, int layout,
+                  float* out);
+/* same on device buffers, asynchronous on cuda_stream (NULL = the engine's stream); plane p of clip c
+ * is written at out_dev + (c*planes + p) * out_stride, out_stride >= info->frames floats */
+int sg_pcm_ingest_device(sg_engine* e, const void* pcm_dev, int64_t n_clips, const sg_pcm_info* info,
+                         int layout, float* out_dev, int64_t out_stride, void* cuda_stream);
+/* Whole path from interleaved PCM on the host: ingest, then sg_stft_batch's pipeline with every plane a
+ * clip.  out: host [n_clips][planes][frames_out][bins] of cfg->output.  The raw bytes (not float32) are
+ * what crosses PCIe; copies, ingest and frame kernels overlap chunk by chunk. */
+int sg_stft_pcm(sg_engine* e, const void* pcm, int64_t n_clips, const sg_pcm_info* info, int layout,
+                const sg_stft_config* cfg, void* out);
+
 /* ------------------------------------------------------------------ sonogram ring + view --- */
 /* The reference's spectrogram history: a bins x rows ALPHA/UNSIGNED_BYTE texture, one byte row per
  * frame written at yoffset, then yoffset = (yoffset + 1) % rows (3D/visualizer.js:60, 301-329,

@@ -7,11 +7,11 @@ Node-API shim for the same ABI live in spectrogram_b200/js.  No CPU fallback.
 from ._lib import (ALIGN_ANALYSER, ALIGN_VALID, OUT_F32_DB, OUT_F32_MAG, OUT_RGBA8, OUT_U8, WINDOW_BLACKMAN,
                    WINDOW_CUSTOM, WINDOW_HANN, WINDOW_RECT, EngineError, IndexSizeError)
 from .analyser import AnalyserNode
-from .api import (Engine, Options, PinnedArray, SonogramRing, StreamBank, colormap_reference, default_engine, device_count,
-                  shard_bounds, spectrogram)
+from .api import (AudioBuffer, Engine, Options, PinnedArray, SonogramRing, StreamBank, colormap_reference, default_engine, device_count,
+                  shard_bounds, spectrogram, wav_info)
 
 __all__ = [
-    "AnalyserNode", "Engine", "Options", "PinnedArray", "StreamBank", "SonogramRing", "spectrogram", "colormap_reference",
+    "AnalyserNode", "AudioBuffer", "wav_info", "Engine", "Options", "PinnedArray", "StreamBank", "SonogramRing", "spectrogram", "colormap_reference",
     "default_engine", "device_count", "shard_bounds", "IndexSizeError", "EngineError",
     "WINDOW_BLACKMAN", "WINDOW_HANN", "WINDOW_RECT", "WINDOW_CUSTOM",
     "OUT_U8", "OUT_F32_DB", "OUT_RGBA8", "OUT_F32_MAG", "ALIGN_VALID", "ALIGN_ANALYSER",

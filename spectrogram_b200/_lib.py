@@ -23,6 +23,8 @@ SG_ERR_STATE = -6
 WINDOW_BLACKMAN, WINDOW_HANN, WINDOW_RECT, WINDOW_CUSTOM = 0, 1, 2, 3
 OUT_U8, OUT_F32_DB, OUT_RGBA8, OUT_F32_MAG = 0, 1, 2, 3
 ALIGN_VALID, ALIGN_ANALYSER = 0, 1
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32 = 0, 1, 2, 3, 4
+PCM_MONO_MIX, PCM_PLANAR = 0, 1
 
 
 class IndexSizeError(ValueError):
@@ -44,6 +46,13 @@ class StftConfig(C.Structure):
         ("min_db", C.c_float), ("max_db", C.c_float), ("smoothing", C.c_float),
         ("custom_window", C.POINTER(C.c_float)), ("colormap", C.POINTER(C.c_uint32)),
     ]
+
+
+class PcmInfo(C.Structure):
+    """``sg_pcm_info``."""
+
+    _fields_ = [("format", C.c_int32), ("channels", C.c_int32), ("sample_rate", C.c_int32),
+                ("frames", C.c_int64), ("data_offset", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/sgcore.h declares
@@ -89,6 +98,14 @@ SIGNATURES = {
     "sg_stream_reset": (C.c_int, [C.c_void_p]),
     "sg_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sg_stream_frames_emitted": (C.c_int64, [C.c_void_p]),
+    "sg_pcm_sample_bytes": (C.c_int, [C.c_int]),
+    "sg_pcm_num_planes": (C.c_int, [C.POINTER(PcmInfo), C.c_int]),
+    "sg_wav_parse": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(PcmInfo)]),
+    "sg_pcm_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PcmInfo), C.c_int, C.c_void_p]),
+    "sg_pcm_ingest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PcmInfo), C.c_int, C.c_void_p,
+                                       C.c_int64, C.c_void_p]),
+    "sg_stft_pcm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PcmInfo), C.c_int, C.POINTER(StftConfig),
+                              C.c_void_p]),
     "sg_ring_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_ring_destroy": (C.c_int, [C.c_void_p]),
     "sg_ring_reset": (C.c_int, [C.c_void_p]),

@@ -69,6 +69,51 @@ class Options:
         return cfg, keep
 
 
+_PCM_FMT = {"u8": L.PCM_U8, "s16": L.PCM_S16, "s24": L.PCM_S24, "s32": L.PCM_S32, "f32": L.PCM_F32}
+_PCM_FMT_OF = {v: k for k, v in _PCM_FMT.items()}
+_PCM_BYTES = {L.PCM_U8: 1, L.PCM_S16: 2, L.PCM_S24: 3, L.PCM_S32: 4, L.PCM_F32: 4}
+
+
+def _pcm_args(data, fmt, channels, sample_rate, n_clips):
+    if fmt not in _PCM_FMT:
+        raise TypeError(f"unknown PCM format {fmt!r}")
+    raw = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else \
+        np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    bpf = int(channels) * _PCM_BYTES[_PCM_FMT[fmt]]
+    if channels < 1 or n_clips < 1 or raw.size % (bpf * n_clips):
+        raise TypeError("PCM byte count is not clips x frames x channels x sample size")
+    info = L.PcmInfo(_PCM_FMT[fmt], int(channels), int(sample_rate), raw.size // (bpf * n_clips), 0)
+    return raw, info
+
+
+def wav_info(file_bytes) -> "L.PcmInfo":
+    """RIFF/WAVE header walk (host only, no GPU): format, channels, sample rate, frames, data offset."""
+    buf = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes
+    info = L.PcmInfo()
+    L.check(L.load().sg_wav_parse(buf.ctypes.data, buf.size, C.byref(info)))
+    return info
+
+
+class AudioBuffer:
+    """What ``decodeAudioData`` hands the reference (util/util.js:10-12): planar float32 channels."""
+
+    def __init__(self, planes: np.ndarray, sample_rate: int):
+        self._planes = planes
+        self.sampleRate = int(sample_rate)
+        self.numberOfChannels = int(planes.shape[-2])
+        self.length = int(planes.shape[-1])
+        self.duration = self.length / self.sampleRate if self.sampleRate else 0.0
+
+    def getChannelData(self, channel: int) -> np.ndarray:
+        if not 0 <= channel < self.numberOfChannels:
+            raise L.IndexSizeError("channel index out of range")
+        return self._planes[..., channel, :]
+
+    @property
+    def planes(self) -> np.ndarray:
+        return self._planes
+
+
 def out_dtype_shape(output: int, n_clips: int, frames: int, bins: int):
     if output == L.OUT_U8:
         return np.uint8, (n_clips, frames, bins)
@@ -154,6 +199,43 @@ class Engine:
             raise TypeError(f"out must be C-contiguous {dt} {shape}")
         L.check(self._lib.sg_stft_batch(self.handle, x.ctypes.data, n_clips, clip_len, C.byref(cfg), out.ctypes.data))
         return out[0] if squeeze else out
+
+    # -- PCM ingestion in front of the path (decodeAudioData for uncompressed PCM) -------------
+    def decode_pcm(self, data, fmt: str = "s16", channels: int = 1, sample_rate: int = 48000, n_clips: int = 1,
+                   mix: bool = False) -> "AudioBuffer":
+        """Interleaved samples (bytes-like or array) -> float32 planes on the GPU.  ``mix=True`` applies the
+        AnalyserNode's speakers down-mix to mono; otherwise every channel is a plane (AudioBuffer.getChannelData)."""
+        raw, info = _pcm_args(data, fmt, channels, sample_rate, n_clips)
+        layout = L.PCM_MONO_MIX if mix else L.PCM_PLANAR
+        planes = 1 if mix else channels
+        out = np.empty((n_clips, planes, info.frames), dtype=np.float32)
+        L.check(self._lib.sg_pcm_ingest(self.handle, raw.ctypes.data, n_clips, C.byref(info), layout, out.ctypes.data))
+        return AudioBuffer(out[0] if n_clips == 1 else out, sample_rate)
+
+    def decode_audio_data(self, file_bytes, mix: bool = False) -> "AudioBuffer":
+        """``context.decodeAudioData(arrayBuffer)`` (util/util.js:9) for RIFF/WAVE files holding uncompressed PCM."""
+        buf = np.frombuffer(bytes(file_bytes) if not isinstance(file_bytes, (bytes, bytearray, memoryview)) else file_bytes,
+                            dtype=np.uint8)
+        info = wav_info(buf)
+        body = buf[info.data_offset:info.data_offset + info.frames * info.channels * _PCM_BYTES[info.format]]
+        return self.decode_pcm(body, _PCM_FMT_OF[info.format], info.channels, info.sample_rate, 1, mix)
+
+    def spectrogram_pcm(self, data, fmt: str = "s16", channels: int = 1, n_clips: int = 1, mix: bool = True,
+                        opts: Options | None = None, **kw) -> np.ndarray:
+        """Interleaved PCM bytes -> [clips, planes, frames, bins(,4)]: ingest fused in front of the batched path
+        (the raw bytes are what crosses PCIe)."""
+        opts = opts or Options(**kw)
+        raw, info = _pcm_args(data, fmt, channels, 0, n_clips)
+        cfg, _keep = opts.to_c()
+        frames = int(self._lib.sg_stft_num_frames(C.byref(cfg), info.frames))
+        if frames < 0:
+            L.check(L.SG_ERR_INDEX_SIZE)
+        planes = 1 if mix else channels
+        dt, shape = out_dtype_shape(cfg.output, n_clips * planes, frames, cfg.n_fft // 2)
+        out = np.empty((n_clips, planes) + shape[1:], dtype=dt)
+        L.check(self._lib.sg_stft_pcm(self.handle, raw.ctypes.data, n_clips, C.byref(info),
+                                      L.PCM_MONO_MIX if mix else L.PCM_PLANAR, C.byref(cfg), out.ctypes.data))
+        return out
 
     # -- batched path on device memory (pointers + a CUDA stream handle) ---------------------
     def spectrogram_device(self, pcm_ptr: int, n_clips: int, clip_len: int, clip_stride: int, opts: Options,

@@ -89,6 +89,12 @@ int launch_wreg_out1(int log2m, const FrameGeom&, const WregPlan&, const Epilogu
 int launch_wreg_out2(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
 int launch_wreg_out3(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
 
+// tu_pcm.cu: PCM ingestion (kernel_pcm.cuh)
+struct PcmGeom;
+struct PcmMix;
+int pcm_tile_frames(int bytes_per_frame);
+int launch_pcm_ingest(int format, const PcmGeom& g, long long n_clips, const PcmMix& m, cudaStream_t st);
+
 constexpr int kMaxDevices = 64;
 
 // one cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per kernel per device

@@ -17,7 +17,9 @@
 #include <vector>
 
 #include "kernel_misc.cuh"
+#include "kernel_pcm.cuh"
 #include "plans.cuh"
+using sg::PcmMix; using sg::PcmGeom; using sg::kPcmMaxChannels; using sg::pcm_tile_frames; using sg::launch_pcm_ingest;
 
 namespace {
 
@@ -327,6 +329,7 @@ struct sg_engine {
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
   DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
+  DevBuf d_raw[2];                   // interleaved PCM bytes in flight (sg_stft_pcm)
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
@@ -589,6 +592,7 @@ int sg_engine_destroy(sg_engine* e) {
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
   e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->d_in.release(); e->d_out.release();
+  e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
   delete e;
@@ -657,8 +661,18 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
 // Host buffers.  Work is cut into chunks (groups of whole clips, or frame ranges of one long clip);
 // chunk i+1's host->device copy and chunk i-1's device->host copy overlap chunk i's kernels on three
 // streams.  Pageable host memory is staged through the engine's pinned bounce buffers.
-int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,
-                  void* out) {
+}  // extern "C"
+
+namespace {
+// Interleaved PCM in front of the pipeline (sg_stft_pcm): the raw bytes are what is copied to the device, an
+// ingest kernel turns each chunk into float32 planes, and every plane is a clip for the frame kernels.
+struct RawPcm {
+  int format, channels, planes, bytes_per_frame;
+  PcmMix mix;
+};
+
+int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,
+                    void* out, const RawPcm* raw) {
   if (!e) return fail(SG_ERR_INVALID_ARG, "engine is null");
   SG_TRY(validate_cfg(cfg));
   if (n_clips < 0 || clip_len < 0) return fail(SG_ERR_INVALID_ARG, "bad clip geometry");
@@ -674,17 +688,18 @@ int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_
   if (frames == 0) return SG_OK;
   const int bins = cfg->n_fft / 2;
   const size_t eb = elem_bytes(cfg->output);
-  const size_t in_bytes = (size_t)n_clips * clip_len * sizeof(float);
-  const size_t out_bytes = (size_t)n_clips * frames * bins * eb;
+  const int planes = raw ? raw->planes : 1;               // device clips per source clip
+  const size_t unit = raw ? (size_t)raw->bytes_per_frame : sizeof(float);   // source bytes per sample frame
+  const size_t out_bytes = (size_t)n_clips * planes * frames * bins * eb;
   // device-resident copies of the whole problem (clip_stride padded to 4 floats for 16-byte rows)
   const long long stride = (clip_len + 3) & ~3LL;
-  SG_TRY(e->d_in.reserve((size_t)n_clips * stride * sizeof(float)));
+  SG_TRY(e->d_in.reserve((size_t)n_clips * planes * stride * sizeof(float)));
   SG_TRY(e->d_out.reserve(out_bytes));
   float* d_in = (float*)e->d_in.p;
   char* d_out = (char*)e->d_out.p;
   float* state = nullptr;
   if (cfg->smoothing != 0.f) {
-    const size_t sb = (size_t)n_clips * bins * sizeof(float);
+    const size_t sb = (size_t)n_clips * planes * bins * sizeof(float);
     SG_TRY(e->scratch_state.reserve(sb));
     SG_CUDA(cudaMemsetAsync(e->scratch_state.p, 0, sb, e->stream));
     state = (float*)e->scratch_state.p;
@@ -693,24 +708,26 @@ int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_
   const size_t kChunk = 32u << 20;  // target bytes per chunk (input side)
   struct Chunk { long long c0, nc, t0, nt; };
   std::vector<Chunk> chunks;
-  const size_t clip_bytes = (size_t)clip_len * sizeof(float);
+  const size_t clip_bytes = (size_t)clip_len * unit;
   if (clip_bytes <= kChunk) {
     const long long per = std::max<long long>(1, (long long)(kChunk / std::max<size_t>(clip_bytes, 1)));
     for (long long c = 0; c < n_clips; c += per) chunks.push_back({c, std::min(per, n_clips - c), 0, frames});
   } else {
-    const long long per = std::max<long long>(1, (long long)(kChunk / ((size_t)cfg->hop * sizeof(float))));
+    const long long per = std::max<long long>(1, (long long)(kChunk / ((size_t)cfg->hop * unit)));
     for (long long c = 0; c < n_clips; ++c)
       for (long long t = 0; t < frames; t += per) chunks.push_back({c, 1, t, std::min(per, frames - t)});
   }
   const long long start_base = cfg->align == SG_ALIGN_VALID ? 0 : (long long)cfg->hop - cfg->n_fft;
   std::vector<cudaEvent_t> ev_in(chunks.size()), ev_k(chunks.size());
   cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};
-  struct Pending { int slot; char* dst; size_t bytes; bool live; } pend[2] = {{0, nullptr, 0, false}, {1, nullptr, 0, false}};
+  // a chunk's output is `rows` runs of `width` bytes, `pitch` apart (one run, or one per plane for a frame range)
+  struct Pending { char* dst; size_t width, pitch; int rows; bool live; } pend[2] = {{nullptr, 0, 0, 0, false}, {nullptr, 0, 0, 0, false}};
   int rc = SG_OK;
   auto drain_out = [&](int slot) -> int {  // copy a finished pinned output bounce to the caller
     if (!pend[slot].live) return SG_OK;
     SG_CUDA(cudaEventSynchronize(ev_pin_out[slot]));
-    std::memcpy(pend[slot].dst, e->pin_out[slot].p, pend[slot].bytes);
+    for (int r = 0; r < pend[slot].rows; ++r)
+      std::memcpy(pend[slot].dst + r * pend[slot].pitch, (char*)e->pin_out[slot].p + r * pend[slot].width, pend[slot].width);
     pend[slot].live = false;
     return SG_OK;
   };
@@ -737,40 +754,67 @@ int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_
         s_hi = std::min<long long>(clip_len, std::max<long long>(s_lo, start_base + (ch.t0 + ch.nt - 1) * cfg->hop + cfg->n_fft));
         uploaded_to = s_hi;
       }
-      const size_t row = (size_t)(s_hi - s_lo) * sizeof(float);
+      const size_t row = (size_t)(s_hi - s_lo) * unit;
       if (row > 0) {
-        const float* src = pcm + ch.c0 * clip_len + s_lo;
+        const char* src = (const char*)pcm + (size_t)ch.c0 * clip_bytes + (size_t)s_lo * unit;
+        char* dst = (char*)(d_in + ch.c0 * stride + s_lo);   // float32 source: straight into the clip rows
+        size_t dpitch = (size_t)stride * sizeof(float);
+        if (raw) {                                            // raw PCM: dense rows in this slot's byte buffer
+          SG_TRY(e->d_raw[slot].reserve(row * ch.nc + 32));
+          if (i >= 2) SG_CUDA(cudaStreamWaitEvent(e->s_h2d, ev_k[i - 2], 0));   // its last reader has finished
+          dst = (char*)e->d_raw[slot].p;
+          dpitch = row;
+        }
         if (!in_pinned) {
           SG_TRY(e->pin_in[slot].reserve(row * ch.nc));
           SG_CUDA(cudaEventSynchronize(ev_pin_in[slot]));   // previous use of this bounce has been copied
           for (long long c = 0; c < ch.nc; ++c)
-            std::memcpy((char*)e->pin_in[slot].p + c * row, src + c * clip_len, row);
-          SG_CUDA(cudaMemcpy2DAsync(d_in + ch.c0 * stride + s_lo, stride * sizeof(float), e->pin_in[slot].p, row, row,
-                                    ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
+            std::memcpy((char*)e->pin_in[slot].p + c * row, src + c * clip_bytes, row);
+          SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, e->pin_in[slot].p, row, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
           SG_CUDA(cudaEventRecord(ev_pin_in[slot], e->s_h2d));
         } else {
-          SG_CUDA(cudaMemcpy2DAsync(d_in + ch.c0 * stride + s_lo, stride * sizeof(float), src, clip_bytes, row, ch.nc,
-                                    cudaMemcpyHostToDevice, e->s_h2d));
+          SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, clip_bytes, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
         }
       }
       SG_CUDA(cudaEventRecord(ev_in[i], e->s_h2d));
       // ---- kernels
       SG_CUDA(cudaStreamWaitEvent(e->stream, ev_in[i], 0));
-      SG_TRY(run_range(e, *pl, *cfg, d_in + ch.c0 * stride, ch.nc, clip_len, stride, ch.t0, ch.nt, frames,
-                       d_out + (size_t)ch.c0 * frames * bins * eb, state ? state + ch.c0 * bins : nullptr, lut, e->stream));
+      if (raw && row > 0) {
+        PcmGeom pg;
+        pg.src = (const unsigned char*)e->d_raw[slot].p;
+        pg.src_bytes = (long long)(row * ch.nc);
+        pg.clip_bytes = (long long)row;
+        pg.frames = s_hi - s_lo;
+        pg.out = d_in + ch.c0 * planes * stride + s_lo;
+        pg.out_stride = stride;
+        pg.tile_frames = pcm_tile_frames(raw->bytes_per_frame);
+        pg.tiles_per_clip = (pg.frames + pg.tile_frames - 1) / pg.tile_frames;
+        pg.channels = raw->channels;
+        pg.planes = planes;
+        SG_CUDA((cudaError_t)launch_pcm_ingest(raw->format, pg, ch.nc, raw->mix, e->stream));
+        e->launches++;
+      }
+      SG_TRY(run_range(e, *pl, *cfg, d_in + ch.c0 * planes * stride, ch.nc * planes, clip_len, stride, ch.t0, ch.nt, frames,
+                       d_out + (size_t)ch.c0 * planes * frames * bins * eb, state ? state + ch.c0 * planes * bins : nullptr,
+                       lut, e->stream));
       SG_CUDA(cudaEventRecord(ev_k[i], e->stream));
       // ---- device -> host
       SG_CUDA(cudaStreamWaitEvent(e->s_d2h, ev_k[i], 0));
-      const size_t off = ((size_t)ch.c0 * frames + ch.t0) * bins * eb;
-      const size_t nbytes = (ch.nt == frames ? (size_t)ch.nc * frames : (size_t)ch.nt) * bins * eb;
+      const size_t off = ((size_t)ch.c0 * planes * frames + ch.t0) * bins * eb;
+      const bool whole = ch.nt == frames;
+      const size_t width = (whole ? (size_t)ch.nc * planes * frames : (size_t)ch.nt) * bins * eb;
+      const int rows = whole ? 1 : planes;
+      const size_t pitch = (size_t)frames * bins * eb;
       if (!out_pinned) {
         SG_TRY(drain_out(slot));
-        SG_TRY(e->pin_out[slot].reserve(nbytes));
-        SG_CUDA(cudaMemcpyAsync(e->pin_out[slot].p, d_out + off, nbytes, cudaMemcpyDeviceToHost, e->s_d2h));
+        SG_TRY(e->pin_out[slot].reserve(width * rows));
+        if (rows == 1) SG_CUDA(cudaMemcpyAsync(e->pin_out[slot].p, d_out + off, width, cudaMemcpyDeviceToHost, e->s_d2h));
+        else SG_CUDA(cudaMemcpy2DAsync(e->pin_out[slot].p, width, d_out + off, pitch, width, rows, cudaMemcpyDeviceToHost, e->s_d2h));
         SG_CUDA(cudaEventRecord(ev_pin_out[slot], e->s_d2h));
-        pend[slot] = {slot, (char*)out + off, nbytes, true};
+        pend[slot] = {(char*)out + off, width, pitch, rows, true};
       } else {
-        SG_CUDA(cudaMemcpyAsync((char*)out + off, d_out + off, nbytes, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (rows == 1) SG_CUDA(cudaMemcpyAsync((char*)out + off, d_out + off, width, cudaMemcpyDeviceToHost, e->s_d2h));
+        else SG_CUDA(cudaMemcpy2DAsync((char*)out + off, pitch, d_out + off, pitch, width, rows, cudaMemcpyDeviceToHost, e->s_d2h));
       }
     }
     SG_TRY(drain_out(0));
@@ -784,10 +828,16 @@ int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_
   for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
   for (auto ev : ev_k) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) { if (ev_pin_in[i]) cudaEventDestroy(ev_pin_in[i]); if (ev_pin_out[i]) cudaEventDestroy(ev_pin_out[i]); }
-  (void)in_bytes;
   return rc;
 }
+}  // namespace
 
+extern "C" {
+int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,
+                  void* out) {
+  return stft_batch_impl(e, pcm, n_clips, clip_len, cfg, out, nullptr);
+}
 }  // extern "C"
 
 #include "sg_objects.inl"
+#include "sg_pcm.inl"

@@ -180,12 +180,73 @@ class SonogramRing {
   }
 }
 
+// What decodeAudioData hands the reference (src/javascripts/util/util.js:10-12, played at UI/player.js:154-170):
+// planar float32 channels.  Produced on the GPU from uncompressed PCM; compressed formats are not decoded here.
+class AudioBuffer {
+  constructor(planes, numberOfChannels, length, sampleRate) {
+    this._planes = planes;                       // Float32Array [channel][frame]
+    this.numberOfChannels = numberOfChannels;
+    this.length = length;
+    this.sampleRate = sampleRate;
+    this.duration = sampleRate ? length / sampleRate : 0;
+  }
+  getChannelData(channel) {
+    if (!(channel >= 0 && channel < this.numberOfChannels)) {
+      const e = new RangeError('channel index out of range');
+      e.code = e.name = 'IndexSizeError';
+      throw e;
+    }
+    return this._planes.subarray(channel * this.length, (channel + 1) * this.length);
+  }
+}
+
+// context.decodeAudioData(arrayBuffer, onBuffer, onError) (util/util.js:9-17) for RIFF/WAVE files holding PCM.
+// Keeps the callback form the reference uses and also returns a Promise, like the browser's.
+function decodeAudioData(arrayBuffer, onBuffer, onError, options) {
+  const o = options || {};
+  return new Promise((resolve, reject) => {
+    try {
+      const file = arrayBuffer instanceof Uint8Array ? arrayBuffer : new Uint8Array(arrayBuffer);
+      const info = guard(native.wavParse)(file);
+      const bytes = info.length * info.channels * { u8: 1, s16: 2, s24: 3, s32: 4, f32: 4 }[info.format];
+      const samples = file.subarray(info.dataOffset, info.dataOffset + bytes);
+      const planes = new Float32Array(info.channels * info.length);
+      guard(native.pcmDecode)(engineFor(o.device || 0), samples, info, 1, 0, planes);
+      const buffer = new AudioBuffer(planes, info.channels, info.length, info.sampleRate);
+      if (onBuffer) onBuffer(buffer);
+      resolve(buffer);
+    } catch (err) {
+      if (onError) onError(err);
+      reject(err);
+    }
+  });
+}
+
+// The frame path fed with interleaved PCM (Uint8Array view of the samples): ingest and, by default, the
+// AnalyserNode's mono down-mix run on the GPU in front of the batched path.
+// pcm = {format: 'u8'|'s16'|'s24'|'s32'|'f32', channels, sampleRate}; returns {frames, bins, planes, data}.
+function spectrogramPcm(samples, pcm, options) {
+  const o = Object.assign({ fftSize: 2048, hop: 512, output: 'u8', mix: true, clips: 1 }, options || {});
+  const bytesPerFrame = (pcm.channels || 1) * { u8: 1, s16: 2, s24: 3, s32: 4, f32: 4 }[pcm.format];
+  const length = Math.floor(samples.length / (bytesPerFrame * o.clips));
+  const frames = guard(native.numFrames)(o, length);
+  const bins = o.fftSize / 2;
+  const planes = o.mix ? 1 : (pcm.channels || 1);
+  const n = o.clips * planes * frames * bins;
+  const data = o.output === 'u8' ? new Uint8Array(n) : (o.output === 'rgba' ? new Uint32Array(n) : new Float32Array(n));
+  guard(native.stftPcm)(engineFor(o.device || 0), samples, pcm, o.clips, o.mix ? 1 : 0, o, data);
+  return { frames, bins, planes, data };
+}
+
 module.exports = {
   AnalyserNode,
   createAnalyser: (options) => new AnalyserNode(options),
   spectrogram,
   StreamBank,
   SonogramRing,
+  AudioBuffer,
+  decodeAudioData,
+  spectrogramPcm,
   colormapReference: () => native.colormapReference(),
   deviceCount: () => native.deviceCount(),
 };

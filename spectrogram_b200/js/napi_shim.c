@@ -462,6 +462,104 @@ static napi_value js_ring_destroy(napi_env env, napi_callback_info info) {
   return undefined_of(env);
 }
 
+/* ---------------------------------------------------------------- PCM ingestion (decodeAudioData for PCM) */
+static const char* const kPcmNames[5] = {"u8", "s16", "s24", "s32", "f32"};
+
+/* wavParse(file: Uint8Array) -> {format, channels, sampleRate, length, dataOffset}: the header walk in front of
+ * context.decodeAudioData (util/util.js:9); host only */
+static napi_value js_wav_parse(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS], o, v;
+  void* bytes;
+  size_t n;
+  sg_pcm_info pi;
+  int rc;
+  if (get_args(env, info, argv) < 1 || !get_typed(env, argv[0], napi_uint8_array, &bytes, &n))
+    return type_error(env, "wavParse(file: Uint8Array)");
+  rc = sg_wav_parse(bytes, n, &pi);
+  if (rc != SG_OK) return throw_status(env, rc);
+  napi_create_object(env, &o);
+  napi_create_string_utf8(env, kPcmNames[pi.format], NAPI_AUTO_LENGTH, &v); napi_set_named_property(env, o, "format", v);
+  napi_create_int32(env, pi.channels, &v); napi_set_named_property(env, o, "channels", v);
+  napi_create_int32(env, pi.sample_rate, &v); napi_set_named_property(env, o, "sampleRate", v);
+  napi_create_double(env, (double)pi.frames, &v); napi_set_named_property(env, o, "length", v);
+  napi_create_double(env, (double)pi.data_offset, &v); napi_set_named_property(env, o, "dataOffset", v);
+  return o;
+}
+
+/* {format, channels, sampleRate} + the byte length of `samples` -> sg_pcm_info for n_clips clips */
+static int parse_pcm(napi_env env, napi_value obj, size_t n_bytes, int32_t n_clips, sg_pcm_info* pi) {
+  napi_valuetype t;
+  double d;
+  char s[8];
+  int bpf;
+  memset(pi, 0, sizeof *pi);
+  pi->format = -1;
+  if (napi_typeof(env, obj, &t) != napi_ok || t != napi_object) { type_error(env, "pcm description must be an object"); return 0; }
+  if (prop_string(env, obj, "format", s, sizeof s))
+    for (int i = 0; i < 5; ++i) if (!strcmp(s, kPcmNames[i])) pi->format = i;
+  if (pi->format < 0) { type_error(env, "format must be one of u8, s16, s24, s32, f32"); return 0; }
+  pi->channels = prop_double(env, obj, "channels", &d) ? (int32_t)d : 1;
+  pi->sample_rate = prop_double(env, obj, "sampleRate", &d) ? (int32_t)d : 0;
+  bpf = pi->channels * sg_pcm_sample_bytes(pi->format);
+  if (pi->channels < 1 || pi->channels > 32 || n_clips < 1 || n_bytes % ((size_t)bpf * (size_t)n_clips)) {
+    type_error(env, "samples length is not clips x frames x channels x sample size");
+    return 0;
+  }
+  pi->frames = (int64_t)(n_bytes / ((size_t)bpf * (size_t)n_clips));
+  return 1;
+}
+
+/* pcmDecode(engine, samples: Uint8Array, pcm, nClips, mix: 0|1, out: Float32Array): interleaved samples ->
+ * float32 planes [clip][plane][frame]; mix = the AnalyserNode's speakers down-mix to mono */
+static napi_value js_pcm_decode(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void *e, *bytes, *out;
+  size_t n, n_out;
+  int32_t n_clips;
+  int32_t mix = 0;
+  sg_pcm_info pi;
+  int rc, planes;
+  if (get_args(env, info, argv) < 6 || !get_external(env, argv[0], &e)) return type_error(env, "pcmDecode(engine, samples, pcm, nClips, mix, out)");
+  if (!get_typed(env, argv[1], napi_uint8_array, &bytes, &n)) return type_error(env, "samples must be a Uint8Array");
+  if (napi_get_value_int32(env, argv[3], &n_clips) != napi_ok) return type_error(env, "nClips must be an integer");
+  if (!parse_pcm(env, argv[2], n, n_clips, &pi)) return undefined_of(env);
+  if (napi_get_value_int32(env, argv[4], &mix) != napi_ok) return type_error(env, "mix must be 0 or 1");
+  if (!get_typed(env, argv[5], napi_float32_array, &out, &n_out)) return type_error(env, "out must be a Float32Array");
+  planes = mix ? 1 : pi.channels;
+  if (n_out < (size_t)n_clips * (size_t)planes * (size_t)pi.frames) return type_error(env, "out is smaller than clips x planes x frames");
+  rc = sg_pcm_ingest((sg_engine*)e, bytes, n_clips, &pi, mix ? SG_PCM_MONO_MIX : SG_PCM_PLANAR, (float*)out);
+  if (rc != SG_OK) return throw_status(env, rc);
+  return undefined_of(env);
+}
+
+/* stftPcm(engine, samples: Uint8Array, pcm, nClips, mix, options, out): the frame path fed with interleaved PCM */
+static napi_value js_stft_pcm(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS];
+  void *e, *bytes, *out;
+  size_t n, n_out;
+  int32_t n_clips;
+  int32_t mix = 1;
+  sg_pcm_info pi;
+  sg_stft_config cfg;
+  int64_t frames;
+  int rc, planes;
+  if (get_args(env, info, argv) < 7 || !get_external(env, argv[0], &e)) return type_error(env, "stftPcm(engine, samples, pcm, nClips, mix, options, out)");
+  if (!get_typed(env, argv[1], napi_uint8_array, &bytes, &n)) return type_error(env, "samples must be a Uint8Array");
+  if (napi_get_value_int32(env, argv[3], &n_clips) != napi_ok) return type_error(env, "nClips must be an integer");
+  if (!parse_pcm(env, argv[2], n, n_clips, &pi)) return undefined_of(env);
+  if (napi_get_value_int32(env, argv[4], &mix) != napi_ok) return type_error(env, "mix must be 0 or 1");
+  if (!parse_config(env, argv[5], &cfg)) return undefined_of(env);
+  frames = sg_stft_num_frames(&cfg, pi.frames);
+  if (frames < 0) return throw_status(env, SG_ERR_INDEX_SIZE);
+  planes = mix ? 1 : pi.channels;
+  if (!get_typed(env, argv[6], sg_stft_elem_bytes(&cfg) == 1 ? napi_uint8_array : (cfg.output == SG_OUT_RGBA8 ? napi_uint32_array : napi_float32_array), &out, &n_out))
+    return type_error(env, "out has the wrong element type for options.output");
+  if (n_out < (size_t)n_clips * (size_t)planes * (size_t)frames * (size_t)(cfg.n_fft / 2)) return type_error(env, "out is smaller than clips x planes x frames x bins");
+  rc = sg_stft_pcm((sg_engine*)e, bytes, n_clips, &pi, mix ? SG_PCM_MONO_MIX : SG_PCM_PLANAR, &cfg, out);
+  if (rc != SG_OK) return throw_status(env, rc);
+  return undefined_of(env);
+}
+
 /* ---------------------------------------------------------------- module init */
 static void export_fn(napi_env env, napi_value exports, const char* name, napi_callback cb) {
   napi_value fn;
@@ -495,6 +593,9 @@ napi_value napi_register_module_v1(napi_env env, napi_value exports) {
   export_fn(env, exports, "ringYoffset", js_ring_yoffset);
   export_fn(env, exports, "ringView", js_ring_view);
   export_fn(env, exports, "ringDestroy", js_ring_destroy);
+  export_fn(env, exports, "wavParse", js_wav_parse);
+  export_fn(env, exports, "pcmDecode", js_pcm_decode);
+  export_fn(env, exports, "stftPcm", js_stft_pcm);
   return exports;
 }
 

@@ -182,7 +182,8 @@ static void cpu_checks(void) {
   const char* names[] = {"deviceCount", "engineCreate", "engineDestroy", "engineLastKernel", "numFrames", "stftBatch",
                          "colormapReference", "analyserCreate", "analyserDestroy", "analyserSet", "analyserGet",
                          "analyserPush", "getByteFrequencyData", "getFloatFrequencyData", "getByteTimeDomainData",
-                         "getFloatTimeDomainData", "streamCreate", "streamPush", "streamDestroy"};
+                         "getFloatTimeDomainData", "streamCreate", "streamPush", "streamDestroy", "ringCreate", "ringAppend",
+                         "ringYoffset", "ringView", "ringDestroy", "wavParse", "pcmDecode", "stftPcm"};
   for (size_t i = 0; i < sizeof names / sizeof *names; ++i) {
     prop* p = find_prop(g_exports, names[i]);
     expect(p && p->value->type == napi_function, names[i]);
@@ -212,6 +213,23 @@ static void cpu_checks(void) {
   a[0] = num(42);
   call("analyserCreate", 1, a);
   expect(threw("TypeError", NULL), "analyserCreate(non-engine) -> TypeError");
+  /* decodeAudioData's header walk (util/util.js:9): a 44-byte canonical header + 3 stereo s16 frames */
+  {
+    static unsigned char wav[56] = {'R','I','F','F', 48,0,0,0, 'W','A','V','E', 'f','m','t',' ', 16,0,0,0, 1,0, 2,0,
+                                    0x44,0xAC,0,0, 0x10,0xB1,2,0, 4,0, 16,0, 'd','a','t','a', 12,0,0,0};
+    a[0] = typed(napi_uint8_array, sizeof wav, wav);
+    r = call("wavParse", 1, a);
+    prop *pf = find_prop(r, "format"), *pc = find_prop(r, "channels"), *ps = find_prop(r, "sampleRate"),
+         *pl = find_prop(r, "length"), *po = find_prop(r, "dataOffset");
+    expect(!g_env.pending && pf && !strcmp(pf->value->str, "s16") && pc->value->num == 2 && ps->value->num == 44100 &&
+               pl->value->num == 3 && po->value->num == 44, "wavParse(stereo s16 header) -> {s16, 2, 44100, 3 frames, offset 44}");
+    wav[20] = 85;                                     /* MPEG layer 3 inside RIFF: not decoded here */
+    call("wavParse", 1, a);
+    expect(threw("TypeError", NULL), "wavParse(compressed WAVE) -> TypeError");
+    a[0] = num(1);
+    call("wavParse", 1, a);
+    expect(threw("TypeError", NULL), "wavParse(non-array) -> TypeError");
+  }
   r = call("deviceCount", 0, NULL);
   if (r->num == 0) {
     a[0] = num(0);
@@ -263,6 +281,31 @@ static void gpu_run(const char* out_path) {
   expect(!g_env.pending && memcmp(row, out + bins, bins) == 0, "analyser.getByteFrequencyData == batch frame 1");
   a[0] = an;
   call("analyserDestroy", 1, a);
+  /* the same clip as 16-bit stereo (L = R = the chirp): mono mix through stftPcm == stftBatch on the quantised clip */
+  {
+    short* s16 = (short*)malloc(sizeof(short) * 2 * n);
+    float* q = (float*)malloc(sizeof(float) * n);
+    float* dec = (float*)malloc(sizeof(float) * n);
+    unsigned char *o1 = (unsigned char*)calloc((size_t)frames * bins, 1), *o2 = (unsigned char*)calloc((size_t)frames * bins, 1);
+    napi_value a7[7], desc = new_value(napi_object);
+    for (int i = 0; i < n; ++i) { s16[2 * i] = s16[2 * i + 1] = (short)lrint(pcm[i] * 32767.0); q[i] = s16[2 * i] / 32768.0f; }
+    napi_set_named_property(&g_env, desc, "format", str("s16"));
+    napi_set_named_property(&g_env, desc, "channels", num(2));
+    a7[0] = eng; a7[1] = typed(napi_uint8_array, sizeof(short) * 2 * n, s16); a7[2] = desc; a7[3] = num(1); a7[4] = num(1);
+    a7[5] = typed(napi_float32_array, n, dec);
+    call("pcmDecode", 6, a7);
+    expect(!g_env.pending && memcmp(dec, q, sizeof(float) * n) == 0, "pcmDecode(s16 stereo, mix) == 0.5(L+R) of v/32768");
+    a7[5] = options(2048, 512, "u8", "valid"); a7[6] = typed(napi_uint8_array, (size_t)frames * bins, o1);
+    call("stftPcm", 7, a7);
+    expect(!g_env.pending, "stftPcm(s16 stereo, mix)");
+    a[0] = eng; a[1] = typed(napi_float32_array, n, q); a[2] = num(1); a[3] = num(n);
+    a[4] = options(2048, 512, "u8", "valid"); a[5] = typed(napi_uint8_array, (size_t)frames * bins, o2);
+    call("stftBatch", 6, a);
+    expect(!g_env.pending && memcmp(o1, o2, (size_t)frames * bins) == 0, "stftPcm bytes == stftBatch bytes of the decoded clip");
+    a7[1] = typed(napi_uint8_array, sizeof(short) * 2 * n - 1, s16);
+    call("stftPcm", 7, a7);
+    expect(threw("TypeError", NULL), "stftPcm with a ragged byte count -> TypeError");
+  }
   FILE* f = fopen(out_path, "wb");
   fwrite(out, 1, (size_t)frames * bins, f);
   fclose(f);

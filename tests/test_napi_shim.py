@@ -33,6 +33,7 @@ def test_addon_exports_only_the_module_entry_point():
     undefined = subprocess.run(["nm", "-D", "--undefined-only", ADDON], capture_output=True, text=True).stdout
     assert "sg_stft_batch" in undefined and "napi_create_function" in undefined
     assert "sg_ring_view" in undefined and "sg_ring_append" in undefined
+    assert "sg_wav_parse" in undefined and "sg_pcm_ingest" in undefined and "sg_stft_pcm" in undefined
 
 
 def test_js_facade_keeps_the_analysernode_surface():
@@ -42,7 +43,8 @@ def test_js_facade_keeps_the_analysernode_surface():
     for name in ("get fftSize", "set fftSize", "get frequencyBinCount", "get minDecibels", "set maxDecibels",
                  "set smoothingTimeConstant", "getByteFrequencyData(array)", "getFloatFrequencyData(array)",
                  "getByteTimeDomainData(array)", "getFloatTimeDomainData(array)", "createAnalyser", "connect(", "IndexSizeError",
-                 "class SonogramRing", "append(frames)", "view(width, height, out)"):
+                 "class SonogramRing", "append(frames)", "view(width, height, out)",
+                 "decodeAudioData(", "class AudioBuffer", "getChannelData(", "numberOfChannels", "spectrogramPcm("):
         assert name in text, name
 
 
