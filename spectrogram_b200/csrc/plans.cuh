@@ -89,6 +89,16 @@ int launch_wreg_out1(int log2m, const FrameGeom&, const WregPlan&, const Epilogu
 int launch_wreg_out2(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
 int launch_wreg_out3(int log2m, const FrameGeom&, const WregPlan&, const Epilogue&, void*, int, int, cudaStream_t);
 
+// tu_w32eo.cu: n_fft 4096 (kernel_w32eo.cuh)
+constexpr int kEoN = 4096;
+struct EoPlan {
+  const float* win;     // [4096]
+  const float2* tw2;    // [31][32] pass-2 twiddles of the 1024-point transform (rows 2^u - 1 are the bases)
+  const float2* tab;    // [32] W_2048^lane, then [16][32] W_4096^{lane + 32 i}
+};
+int launch_w32eo(int out_kind, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
+                 int device, cudaStream_t st);
+
 // tu_pcm.cu: PCM ingestion (kernel_pcm.cuh)
 struct PcmGeom;
 struct PcmMix;

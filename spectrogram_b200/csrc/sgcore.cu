@@ -68,6 +68,7 @@ struct Plan {
   int* pos = nullptr;
   float2* w32_tw2 = nullptr;  // lane-major stage 6-10 twiddles (powers of two, 256 <= n_fft <= 8192)
   float2* w32_ut = nullptr;   // only n_fft == 2048
+  float2* eo_tab = nullptr;   // only n_fft == 4096: W_2048^lane, then W_4096^{lane + 32 i}
   float2* wreg_tw3 = nullptr; // lane-major stage 11-12 twiddles (n_fft 4096, 8192)
   float2* pair_twb = nullptr; // n_fft 1024 / 512: pass-2 base twiddles of the part-warp pair kernels [log2 L][32]
   float2* w16_tw = nullptr;   // n_fft == 512: pass-2 twiddles of the 16 x 16 kernel [15][16]
@@ -75,7 +76,7 @@ struct Plan {
   float2* r400_ut = nullptr;  // n_fft == 400: W_400^k [200]
   int log2m = 0;              // log2(n_fft/2) when n_fft is a power of two, else 0
   void release() {
-    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(wreg_tw3); cudaFree(pair_twb); cudaFree(w16_tw); cudaFree(r400_tw); cudaFree(r400_ut);
+    cudaFree(win); cudaFree(tw); cudaFree(ut); cudaFree(pos); cudaFree(w32_tw2); cudaFree(w32_ut); cudaFree(eo_tab); cudaFree(wreg_tw3); cudaFree(pair_twb); cudaFree(w16_tw); cudaFree(r400_tw); cudaFree(r400_ut);
   }
 };
 
@@ -199,6 +200,13 @@ int build_plan(const sg_stft_config& cfg, Plan& p) {
     for (int k = 0; k < 200; ++k) ut4[k] = expi((double)k / 400.0);
     SG_TRY(upload(&p.r400_tw, tw5));
     SG_TRY(upload(&p.r400_ut, ut4));
+  }
+  if (n == sg::kEoN) {
+    std::vector<float2> tab(32 + 16 * 32);
+    for (int lane = 0; lane < 32; ++lane) tab[lane] = expi((double)lane / 2048.0);
+    for (int i = 0; i < 16; ++i)
+      for (int lane = 0; lane < 32; ++lane) tab[32 + i * 32 + lane] = expi((double)(lane + 32 * i) / n);
+    SG_TRY(upload(&p.eo_tab, tab));
   }
   if (n == sg::kW32N) {
     std::vector<float2> ut32(16 * 32);
@@ -386,6 +394,10 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32";
+  } else if (pl.n_fft == sg::kEoN && v == 0 && x2_ok) {
+    const sg::EoPlan eo{pl.win, pl.w32_tw2, pl.eo_tab};
+    rc = sg::launch_w32eo(out_kind, g, eo, ep, out, e->sm_count, e->device, st);
+    e->last_kernel = "eo4096";
   } else if (pl.n_fft == 400 && v != 1) {
     const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};
     rc = sg::launch_r400(out_kind, g, rp, ep, out, e->sm_count, e->device, st);
