@@ -100,6 +100,17 @@ struct sg_stream {
   PinBuf h_in, h_out, h_rgba;
   int cur = 0;
   int64_t frames_emitted = 0;
+  // Off the critical path of a push: the history slide runs on a side stream beside the frame kernel, and the byte
+  // rows leave on the copy stream while the colour LUT kernel runs.
+  cudaEvent_t ev_in = nullptr, ev_frames = nullptr, ev_slide = nullptr, ev_bytes = nullptr;
+  bool slide_pending = false;
+  const void* pinned_seen[3] = {nullptr, nullptr, nullptr};   // caller buffers already known to be page-locked
+  bool pinned(const void* p, int slot) {
+    if (p == pinned_seen[slot]) return true;
+    if (!is_pinned(p)) return false;
+    pinned_seen[slot] = p;
+    return true;
+  }
 };
 
 struct sg_ring {
@@ -244,6 +255,7 @@ int sg_stream_reset(sg_stream* s) {
   if (!s) return fail(SG_ERR_INVALID_ARG, "stream is null");
   std::lock_guard<std::mutex> lock(s->e->mu);
   SG_CUDA(cudaSetDevice(s->e->device));
+  if (s->slide_pending) { SG_CUDA(cudaEventSynchronize(s->ev_slide)); s->slide_pending = false; }
   for (int i = 0; i < 2; ++i) SG_CUDA(cudaMemsetAsync(s->hist[i].p, 0, s->hist[i].cap, s->e->stream));
   SG_CUDA(cudaMemsetAsync(s->d_state.p, 0, s->d_state.cap, s->e->stream));
   s->cur = 0;
@@ -295,6 +307,9 @@ int sg_stream_destroy(sg_stream* s) {
     std::lock_guard<std::mutex> lock(s->e->mu);
     cudaSetDevice(s->e->device);
     cudaStreamSynchronize(s->e->stream);
+    cudaStreamSynchronize(s->e->s_h2d);
+    cudaStreamSynchronize(s->e->s_d2h);
+    for (cudaEvent_t ev : {s->ev_in, s->ev_frames, s->ev_slide, s->ev_bytes}) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) s->hist[i].release();
     s->d_out.release(); s->d_rgba.release(); s->d_state.release();
     s->h_in.release(); s->h_out.release(); s->h_rgba.release();
@@ -321,14 +336,26 @@ int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, u
   const size_t eb = elem_bytes(c.output);
   float* hist = (float*)s->hist[s->cur].p;
   float* next = (float*)s->hist[s->cur ^ 1].p;
+  if (!s->ev_in) {
+    for (cudaEvent_t* ev : {&s->ev_in, &s->ev_frames, &s->ev_slide, &s->ev_bytes})
+      SG_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  }
   // new samples land behind the n_fft samples of history: row = [history | chunk]
   const float* src = chunk;
-  if (!is_pinned(chunk)) {
+  if (!s->pinned(chunk, 0)) {
     std::memcpy(s->h_in.p, chunk, sizeof(float) * (size_t)chunk_len * ch);
     src = (const float*)s->h_in.p;
   }
+  if (s->slide_pending) SG_CUDA(cudaStreamWaitEvent(st, s->ev_slide, 0));   // this history row set is being written
   SG_CUDA(cudaMemcpy2DAsync(hist + n, s->pitch * sizeof(float), src, (size_t)chunk_len * sizeof(float),
                             (size_t)chunk_len * sizeof(float), ch, cudaMemcpyHostToDevice, st));
+  SG_CUDA(cudaEventRecord(s->ev_in, st));
+  // slide the history beside the frame kernel: the last n_fft samples of [history | chunk] become the next history
+  SG_CUDA(cudaStreamWaitEvent(e->s_h2d, s->ev_in, 0));
+  SG_CUDA(cudaMemcpy2DAsync(next, s->pitch * sizeof(float), hist + chunk_len, s->pitch * sizeof(float),
+                            (size_t)n * sizeof(float), ch, cudaMemcpyDeviceToDevice, e->s_h2d));
+  SG_CUDA(cudaEventRecord(s->ev_slide, e->s_h2d));
+  s->slide_pending = true;
   // frame t ends at history + (t+1)*hop: with the row shifted by hop it is the "valid" geometry
   Plan* pl;
   SG_TRY(e->get_plan(c, &pl));
@@ -337,21 +364,24 @@ int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, u
   SG_TRY(run_range(e, *pl, c, hist + c.hop, ch, (long long)n + chunk_len - c.hop, s->pitch, 0, frames, frames,
                    s->d_out.p, (float*)s->d_state.p, lut, st));
   const size_t n_out = (size_t)ch * frames * bins;
+  const bool out_pin = s->pinned(out, 1), rgba_pin = out_rgba && s->pinned(out_rgba, 2);
   if (out_rgba) {
+    // the byte rows go home on the copy stream while the LUT kernel expands them
+    SG_CUDA(cudaEventRecord(s->ev_frames, st));
+    SG_CUDA(cudaStreamWaitEvent(e->s_d2h, s->ev_frames, 0));
+    SG_CUDA(cudaMemcpyAsync(out_pin ? out : s->h_out.p, s->d_out.p, n_out * eb, cudaMemcpyDeviceToHost, e->s_d2h));
+    SG_CUDA(cudaEventRecord(s->ev_bytes, e->s_d2h));
     sg::lut_kernel<<<(unsigned)std::min<size_t>((n_out + 255) / 256, 148 * 8), 256, 0, st>>>(
         (const uint8_t*)s->d_out.p, (uint32_t*)s->d_rgba.p, (long long)n_out, lut);
     e->launches++;
     SG_CUDA(cudaGetLastError());
-  }
-  const bool out_pin = is_pinned(out), rgba_pin = out_rgba && is_pinned(out_rgba);
-  SG_CUDA(cudaMemcpyAsync(out_pin ? out : s->h_out.p, s->d_out.p, n_out * eb, cudaMemcpyDeviceToHost, st));
-  if (out_rgba)
     SG_CUDA(cudaMemcpyAsync(rgba_pin ? (void*)out_rgba : s->h_rgba.p, s->d_rgba.p, n_out * 4, cudaMemcpyDeviceToHost, st));
-  // slide the history: the last n_fft samples of [history | chunk] become the next history
-  SG_CUDA(cudaMemcpy2DAsync(next, s->pitch * sizeof(float), hist + chunk_len, s->pitch * sizeof(float),
-                            (size_t)n * sizeof(float), ch, cudaMemcpyDeviceToDevice, st));
+  } else {
+    SG_CUDA(cudaMemcpyAsync(out_pin ? out : s->h_out.p, s->d_out.p, n_out * eb, cudaMemcpyDeviceToHost, st));
+  }
   s->cur ^= 1;
   SG_CUDA(cudaStreamSynchronize(st));
+  if (out_rgba) SG_CUDA(cudaEventSynchronize(s->ev_bytes));
   if (!out_pin) std::memcpy(out, s->h_out.p, n_out * eb);
   if (out_rgba && !rgba_pin) std::memcpy(out_rgba, s->h_rgba.p, n_out * 4);
   s->frames_emitted += frames;
