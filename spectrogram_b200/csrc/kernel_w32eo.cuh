@@ -269,8 +269,16 @@ stft_w32eo_kernel(FrameGeom g, EoPlan pl, Epilogue ep, typename OutElem<OUT>::ty
         const int k = lane + 32 * i;
         int mk = 1024 - k;
         if constexpr (i == 0) { if (lane0) mk = 512; }
-        row_lo[k] = emit_power<OUT>(pk[i].v.x, ep); row_hi[k] = emit_power<OUT>(pk[i].v.y, ep);
-        row_hi[mk] = emit_power<OUT>(pm[i].v.x, ep); row_lo[mk] = emit_power<OUT>(pm[i].v.y, ep);
+        if constexpr (OUT == kOutF32Db) {
+          // packed dB; the non-finite rule from the per-frame flag (a poisoned frame reads -inf)
+          const bool bad = !(poison.v.x == 0.f);
+          const P2 vk = db_of_power(pk[i], ep), vm = db_of_power(pm[i], ep);
+          row_lo[k] = bad ? neg_inf() : vk.v.x; row_hi[k] = bad ? neg_inf() : vk.v.y;
+          row_hi[mk] = bad ? neg_inf() : vm.v.x; row_lo[mk] = bad ? neg_inf() : vm.v.y;
+        } else {
+          row_lo[k] = emit_power<OUT>(pk[i].v.x, ep); row_hi[k] = emit_power<OUT>(pk[i].v.y, ep);
+          row_hi[mk] = emit_power<OUT>(pm[i].v.x, ep); row_lo[mk] = emit_power<OUT>(pm[i].v.y, ep);
+        }
         s[16 + i] = ldg_nc_f4(nsrc + 32 * elem_of(16 + i));
       });
     }

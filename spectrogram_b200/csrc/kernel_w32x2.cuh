@@ -107,6 +107,12 @@ __device__ __forceinline__ unsigned byte_of_scaled(float v) {
   asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(v));
   return b;
 }
+// float dB of one power pair: db_scale * lg2(p) + db_off, packed (lg2.approx.ftz: powers below 2^-126 read as 0)
+__device__ __forceinline__ P2 db_of_power(P2 p, const Epilogue& ep) {
+  return fma2(P2(lg2_ftz(p.v.x), lg2_ftz(p.v.y)), bc(ep.db_scale), bc(ep.db_off));
+}
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
 // byte path for one power pair (tau == 0):
 //   q = p*0 + p        finite p -> p ; Inf/NaN -> NaN      ([SPEC] non-finite -> 0, via cvt(NaN) = 0)
 //   v = a*lg2(q) + b   ; byte = cvt.rzi.u8.f32(v)
@@ -305,6 +311,9 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
     dit2_stage_table<4>(a, tw_lane);
     dit2_stage_table<5>(a, tw_lane);
     // now a[i] = Z[lane + 32 i] of both frames
+    // a non-finite sample makes every Z of its frame non-finite: one flag per frame for the float dB path
+    const P2 poison = fma2(a[0].re, bc(0.f), mul2(a[0].im, bc(0.f)));   // 0 or NaN per frame
+    const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
 
     // ---- untangle exchange: upper half (k >= 512) to smem at index k - 512; Z[1024] == Z[0] at 512.
     //      re pairs at xp[0..513), im pairs at xp[520..1033)
@@ -358,6 +367,11 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
         bytes_of_power(pm[i], ep, ma, mb);
         row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
         if (cur.has_b) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
+      } else if constexpr (OUT == kOutF32Db) {
+        // the non-finite rule from the per-frame flag: a poisoned frame reads -inf (the dB of magnitude 0)
+        const P2 vk = db_of_power(pk[i], ep), vm = db_of_power(pm[i], ep);
+        row_a[k] = bad_a ? neg_inf() : vk.v.x; row_a[mk] = bad_a ? neg_inf() : vm.v.x;
+        if (cur.has_b) { row_b[k] = bad_b ? neg_inf() : vk.v.y; row_b[mk] = bad_b ? neg_inf() : vm.v.y; }
       } else {
         row_a[k] = emit_power<OUT>(pk[i].v.x, ep); row_a[mk] = emit_power<OUT>(pm[i].v.x, ep);
         if (cur.has_b) { row_b[k] = emit_power<OUT>(pk[i].v.y, ep); row_b[mk] = emit_power<OUT>(pm[i].v.y, ep); }
