@@ -56,6 +56,18 @@ __device__ __forceinline__ unsigned byte_from_scaled(float v) {
   return (unsigned)v;               // truncation, as static_cast<unsigned char> in Chromium
 }
 
+__device__ __forceinline__ float lg2_ftz(float x) {  // MUFU.LG2 alone: subnormal inputs read as 0 (-inf)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// cvt.rzi.u8.f32 saturates to [0, 255] and maps NaN to 0: the clamp of step 6 in one instruction
+__device__ __forceinline__ unsigned byte_of_scaled(float v) {
+  unsigned b;
+  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(v));
+  return b;
+}
+
 // from unnormalised power p = re^2 + im^2  (tau == 0 path: no sqrt needed); the caller has already applied the
 // non-finite rule (kernels that decide it once per frame)
 template <int OUT>
@@ -63,11 +75,10 @@ __device__ __forceinline__ typename OutElem<OUT>::type emit_power_finite(float p
   if constexpr (OUT == kOutF32Mag) {
     return sqrtf(p) * e.mag_scale;
   } else {
-    const float l = __log2f(p);
     if constexpr (OUT == kOutF32Db) {
-      return fmaf(e.db_scale, l, e.db_off);
+      return fmaf(e.db_scale, lg2_ftz(p), e.db_off);      // powers below 2^-126 (|X|/N < 1e-19) read as 0: -inf dB
     } else {
-      const unsigned b = byte_from_scaled(fmaf(e.byte_a, l, e.byte_b));
+      const unsigned b = byte_of_scaled(fmaf(e.byte_a, __log2f(p), e.byte_b));   // exact for any minDecibels
       if constexpr (OUT == kOutU8) return (uint8_t)b;
       else return __ldg(e.lut + b);
     }

@@ -96,17 +96,6 @@ __device__ __forceinline__ void dit2_stage_table(C2 (&a)[32], const float2* __re
 }
 
 // ---------------------------------------------------------------- epilogue helpers
-__device__ __forceinline__ float lg2_ftz(float x) {  // MUFU.LG2 alone: subnormal inputs read as 0 (-inf)
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// cvt.rzi.u8.f32 saturates to [0, 255] and maps NaN to 0: the clamp of step 6 in one instruction
-__device__ __forceinline__ unsigned byte_of_scaled(float v) {
-  unsigned b;
-  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(v));
-  return b;
-}
 // float dB of one power pair: db_scale * lg2(p) + db_off, packed (lg2.approx.ftz: powers below 2^-126 read as 0)
 __device__ __forceinline__ P2 db_of_power(P2 p, const Epilogue& ep) {
   return fma2(P2(lg2_ftz(p.v.x), lg2_ftz(p.v.y)), bc(ep.db_scale), bc(ep.db_off));
