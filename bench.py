@@ -301,7 +301,7 @@ def run_gpu(args) -> None:
     float_db = None
     if world == 1:
         opts_db = sg.Options(fftSize=N_FFT, hop=HOP, window="blackman", output="db")
-        n_db = min(plan["n_clips"], 256)
+        n_db = min(plan["n_clips"], 512)
         out_db = torch.empty((n_db, frames_per_clip, N_FFT // 2), dtype=torch.float32, device=dev)
 
         def step_db():

@@ -98,7 +98,7 @@ int sg_engine_device(const sg_engine* e);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 int64_t sg_engine_launch_count(const sg_engine* e);
 /* name of the kernel family the last sg_stft_* call on this engine used
- * ("warp32x32x2p", "warp32x32x2", "warp32x32", "wreg", "r400", "smem") */
+ * ("warp32x32x2p", "warp32x32x2", "warp32x32", "eo4096", "p16", "p8", "p4", "w16", "wreg", "r400", "smem") */
 const char* sg_engine_last_kernel(const sg_engine* e);
 
 /* ------------------------------------------------------------------ batched path ----------- */

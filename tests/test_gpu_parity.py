@@ -87,7 +87,7 @@ def test_config1_chirp_full(engine):
         for align in (O.ALIGN_VALID, O.ALIGN_ANALYSER):
             cfg = O.Config(window=window, align=align)
             check_all_outputs(engine, x, cfg)
-            assert engine.last_kernel == "warp32x32x2p"
+            assert engine.last_kernel in ("warp32x32x2p", "warp32x32x2")   # float dB rows take the TMA-staged kernel
     assert engine.spectrogram(x, sg.Options()).shape == (858, 1024)
     assert engine.spectrogram(x, sg.Options(align="analyser")).shape == (861, 1024)
 
