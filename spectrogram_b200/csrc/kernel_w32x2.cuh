@@ -303,6 +303,7 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
     // a non-finite sample makes every Z of its frame non-finite: one flag per frame for the float dB path
     const P2 poison = fma2(a[0].re, bc(0.f), mul2(a[0].im, bc(0.f)));   // 0 or NaN per frame
     const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
+    const P2 byte_scale = add2(bc(ep.byte_a), poison);
 
     // ---- untangle exchange: upper half (k >= 512) to smem at index k - 512; Z[1024] == Z[0] at 512.
     //      re pairs at xp[0..513), im pairs at xp[520..1033)
@@ -345,15 +346,18 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
       int mk = kW32M - k;
       if constexpr (i == 0) { if (special) mk = 512; }
       if constexpr (OUT == kOutU8) {
-        unsigned ka, kb, ma, mb;
-        bytes_of_power(pk[i], ep, ka, kb);
-        bytes_of_power(pm[i], ep, ma, mb);
+        // the per-frame non-finite flag rides in the byte scale: NaN scale -> NaN -> byte 0
+        const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), byte_scale, bc(ep.byte_b));
+        const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), byte_scale, bc(ep.byte_b));
+        const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
+        const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
         sb16[k] = (uint16_t)(ka | (kb << 8));
         sb16[mk] = (uint16_t)(ma | (mb << 8));
       } else if constexpr (OUT == kOutRgba8) {
-        unsigned ka, kb, ma, mb;
-        bytes_of_power(pk[i], ep, ka, kb);
-        bytes_of_power(pm[i], ep, ma, mb);
+        const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), byte_scale, bc(ep.byte_b));
+        const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), byte_scale, bc(ep.byte_b));
+        const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
+        const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
         row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
         if (cur.has_b) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
       } else if constexpr (OUT == kOutF32Db) {
