@@ -58,8 +58,9 @@ for v in args.variants:
         d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         par = f"max {d.max()} LSB, mismatch {float((d != 0).mean()):.2e}"
     else:
-        fin = np.isfinite(ref) & (ref > -150)
-        par = f"max dB err {np.abs(got[fin] - ref[fin]).max():.2e}"
+        # the tolerance of tests/_tol.py: 1e-3 dB on bins within 50 dB of their frame's peak
+        near = np.isfinite(ref) & (ref >= ref.max(axis=-1, keepdims=True) - 50.0)
+        par = f"max dB err within 50 dB of the frame peak {np.abs(got[near] - ref[near]).max():.2e}"
     fps = args.clips * fpc / ms * 1e3
     print(f"variant {v} [{eng.last_kernel}] {ms:.4f} ms  {fps / 1e6:.1f} Mframes/s  hbm {fps * bpf / 6551.4e9:.3f}  parity: {par}", flush=True)
 eng.close()
