@@ -96,4 +96,33 @@ pcm_ingest_kernel(const __grid_constant__ PcmGeom g, const __grid_constant__ Pcm
   }
 }
 
+// ---- 16-bit fast path (the common case): when source rows, destination rows and the frame count are 16-byte
+// friendly, every thread converts one 16-byte word (8 samples) straight from global memory: no shared-memory stage.
+//   MODE 0: mono -> 1 plane (8 frames per word);  1: stereo -> mono mix 0.5(L+R) (4 frames);  2: stereo -> 2 planes
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pcm_s16_vec_kernel(const uint4* __restrict__ src, long long words_per_clip, long long n_clips, float* __restrict__ out,
+                   long long out_stride) {
+  constexpr float k = 1.f / 32768.f;
+  const long long total = words_per_clip * n_clips;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long clip = i / words_per_clip, w = i - clip * words_per_clip;
+    const uint4 q = __ldg(src + i);
+    auto lo = [](uint32_t v) { return (float)(short)(v & 0xffffu); };
+    auto hi = [](uint32_t v) { return (float)((int)v >> 16); };
+    if constexpr (MODE == 0) {
+      float4* d = reinterpret_cast<float4*>(out + clip * out_stride) + 2 * w;
+      d[0] = make_float4(lo(q.x) * k, hi(q.x) * k, lo(q.y) * k, hi(q.y) * k);
+      d[1] = make_float4(lo(q.z) * k, hi(q.z) * k, lo(q.w) * k, hi(q.w) * k);
+    } else if constexpr (MODE == 1) {
+      auto mix = [&](uint32_t v) { return fmaf(0.5f, hi(v) * k, 0.5f * (lo(v) * k)); };   // as the generic kernel: w0 x0, then FMA
+      reinterpret_cast<float4*>(out + clip * out_stride)[w] = make_float4(mix(q.x), mix(q.y), mix(q.z), mix(q.w));
+    } else {
+      float* base = out + 2 * clip * out_stride;
+      reinterpret_cast<float4*>(base)[w] = make_float4(lo(q.x) * k, lo(q.y) * k, lo(q.z) * k, lo(q.w) * k);
+      reinterpret_cast<float4*>(base + out_stride)[w] = make_float4(hi(q.x) * k, hi(q.y) * k, hi(q.z) * k, hi(q.w) * k);
+    }
+  }
+}
+
 }  // namespace sg

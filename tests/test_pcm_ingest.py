@@ -158,6 +158,20 @@ def test_planes_are_bit_exact_and_mono_mix_follows_the_speakers_rules(engine, fm
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("channels,mix", [(1, True), (2, True), (2, False)])
+@pytest.mark.parametrize("frames,n_clips", [(20000, 1), (4096, 5), (8, 3)])
+def test_sixteen_bit_vector_path_is_bit_exact(engine, channels, mix, frames, n_clips):
+    """16-byte friendly 16-bit mono/stereo takes the one-word-per-thread kernel: same results as the oracle"""
+    raw = np.frombuffer(random_pcm(po.S16, channels, frames * n_clips, seed=frames + channels), dtype="<i2").copy()
+    assert raw.ctypes.data % 16 == 0
+    got = engine.decode_pcm(raw, "s16", channels, 48000, n_clips=n_clips, mix=mix).planes.reshape(n_clips, -1, frames)
+    for c in range(n_clips):
+        want = po.decode_interleaved(raw[c * frames * channels:(c + 1) * frames * channels].tobytes(), po.S16, channels)
+        ref = po.downmix_speakers(want)[None] if mix else want
+        np.testing.assert_array_equal(got[c], ref.astype(np.float32))
+
+
+@pytest.mark.gpu
 def test_ingest_handles_unaligned_sources_many_clips_and_empty_input(engine):
     raw = random_pcm(po.S24, 2, 3 * 5000, seed=5)   # three clips of 5000 frames, 6-byte frames
     pad = np.frombuffer(b"\x55" * 3 + raw, dtype=np.uint8)[3:]     # source pointer at an odd address
