@@ -56,6 +56,11 @@ __device__ __forceinline__ unsigned byte_from_scaled(float v) {
   return (unsigned)v;               // truncation, as static_cast<unsigned char> in Chromium
 }
 
+__device__ __forceinline__ float sqrt_ftz(float x) {  // MUFU.SQRT alone (2^-23 relative), subnormal inputs read as 0
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lg2_ftz(float x) {  // MUFU.LG2 alone: subnormal inputs read as 0 (-inf)
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -73,7 +78,7 @@ __device__ __forceinline__ unsigned byte_of_scaled(float v) {
 template <int OUT>
 __device__ __forceinline__ typename OutElem<OUT>::type emit_power_finite(float p, const Epilogue& e) {
   if constexpr (OUT == kOutF32Mag) {
-    return sqrtf(p) * e.mag_scale;
+    return sqrt_ftz(p) * e.mag_scale;
   } else {
     if constexpr (OUT == kOutF32Db) {
       return fmaf(e.db_scale, lg2_ftz(p), e.db_off);      // powers below 2^-126 (|X|/N < 1e-19) read as 0: -inf dB

@@ -310,17 +310,15 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
         constexpr int i = decltype(ii)::value;
         int k, mk;
         bins_of(ii, k, mk);
-        if constexpr (OUT == kOutF32Db) {
-          // packed dB; the non-finite rule from the per-frame flag (a poisoned frame reads -inf)
+        {
+          // packed dB / magnitude; the non-finite rule from the per-frame flag (a poisoned frame reads 0 / -inf)
           const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
-          const P2 vk = db_of_power(pk[i], ep), vm = db_of_power(pm[i], ep);
+          const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
+          const float z = float_of_poisoned<OUT>();
           if (alive) {
-            row_a[k] = bad_a ? neg_inf() : vk.v.x; row_a[mk] = bad_a ? neg_inf() : vm.v.x;
-            if (has_b_out) { row_b[k] = bad_b ? neg_inf() : vk.v.y; row_b[mk] = bad_b ? neg_inf() : vm.v.y; }
+            row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
+            if (has_b_out) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
           }
-        } else if (alive) {
-          row_a[k] = emit_power<OUT>(pk[i].v.x, ep); row_a[mk] = emit_power<OUT>(pm[i].v.x, ep);
-          if (has_b_out) { row_b[k] = emit_power<OUT>(pk[i].v.y, ep); row_b[mk] = emit_power<OUT>(pm[i].v.y, ep); }
         }
       });
     }

@@ -101,6 +101,15 @@ __device__ __forceinline__ P2 db_of_power(P2 p, const Epilogue& ep) {
   return fma2(P2(lg2_ftz(p.v.x), lg2_ftz(p.v.y)), bc(ep.db_scale), bc(ep.db_off));
 }
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+// float outputs of one power pair: dB as above, or the linear magnitude sqrt(p) * mag_scale; and what a frame with a
+// non-finite sample reads in that output ([SPEC] magnitude 0: -inf dB)
+template <int OUT>
+__device__ __forceinline__ P2 float_of_power(P2 p, const Epilogue& ep) {
+  if constexpr (OUT == kOutF32Db) return db_of_power(p, ep);
+  else return mul2(P2(sqrt_ftz(p.v.x), sqrt_ftz(p.v.y)), bc(ep.mag_scale));
+}
+template <int OUT>
+__device__ __forceinline__ float float_of_poisoned() { return OUT == kOutF32Db ? neg_inf() : 0.f; }
 
 // byte path for one power pair (tau == 0):
 //   q = p*0 + p        finite p -> p ; Inf/NaN -> NaN      ([SPEC] non-finite -> 0, via cvt(NaN) = 0)
@@ -360,14 +369,12 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
         const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
         row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
         if (cur.has_b) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
-      } else if constexpr (OUT == kOutF32Db) {
-        // the non-finite rule from the per-frame flag: a poisoned frame reads -inf (the dB of magnitude 0)
-        const P2 vk = db_of_power(pk[i], ep), vm = db_of_power(pm[i], ep);
-        row_a[k] = bad_a ? neg_inf() : vk.v.x; row_a[mk] = bad_a ? neg_inf() : vm.v.x;
-        if (cur.has_b) { row_b[k] = bad_b ? neg_inf() : vk.v.y; row_b[mk] = bad_b ? neg_inf() : vm.v.y; }
       } else {
-        row_a[k] = emit_power<OUT>(pk[i].v.x, ep); row_a[mk] = emit_power<OUT>(pm[i].v.x, ep);
-        if (cur.has_b) { row_b[k] = emit_power<OUT>(pk[i].v.y, ep); row_b[mk] = emit_power<OUT>(pm[i].v.y, ep); }
+        // float dB / magnitude, packed; the non-finite rule from the per-frame flag (magnitude 0: -inf dB)
+        const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
+        const float z = float_of_poisoned<OUT>();
+        row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
+        if (cur.has_b) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
       }
     });
     if constexpr (OUT == kOutU8) {

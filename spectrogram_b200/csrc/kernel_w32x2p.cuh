@@ -324,29 +324,22 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
           if (has_b_out) rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
         }
       }
-    } else if constexpr (OUT == kOutF32Db) {
-      // dB = db_scale * lg2(p) + db_off, packed; the non-finite rule is one select per value on the per-frame flag
-      // (a poisoned frame reads -inf, the dB of magnitude 0).  lg2.approx.ftz: powers below 2^-126 read as 0.
-      // (Measured slower, 510-511 vs 529 M frames/s: a warp-uniform branch around a select-free copy of this loop,
+    } else {
+      // float dB (db_scale * lg2(p) + db_off) or magnitude (sqrt(p) * mag_scale), packed; the non-finite rule is one
+      // select per value on the per-frame flag (a poisoned frame reads magnitude 0 / -inf dB).  The approx.ftz forms:
+      // powers below 2^-126 read as 0.
+      // (Measured slower, 510-511 vs 529 M frames/s in dB: a warp-uniform branch around a select-free copy of this loop,
       //  and select-free stores followed by a cold loop that overwrites a poisoned frame's rows.)
       const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
+      const float z = float_of_poisoned<OUT>();
       static_for<0, 16>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
         const int k = lane + 32 * i;
         int mk = kW32M - k;
         if constexpr (i == 0) { if (lane0) mk = 512; }
-        const P2 vk = db_of_power(pk[i], ep), vm = db_of_power(pm[i], ep);
-        row_a[k] = bad_a ? neg_inf() : vk.v.x; row_a[mk] = bad_a ? neg_inf() : vm.v.x;
-        if (has_b_out) { row_b[k] = bad_b ? neg_inf() : vk.v.y; row_b[mk] = bad_b ? neg_inf() : vm.v.y; }
-      });
-    } else {
-      static_for<0, 16>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int k = lane + 32 * i;
-        int mk = kW32M - k;
-        if constexpr (i == 0) { if (lane0) mk = 512; }
-        row_a[k] = emit_power<OUT>(pk[i].v.x, ep); row_a[mk] = emit_power<OUT>(pm[i].v.x, ep);
-        if (has_b_out) { row_b[k] = emit_power<OUT>(pk[i].v.y, ep); row_b[mk] = emit_power<OUT>(pm[i].v.y, ep); }
+        const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
+        row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
+        if (has_b_out) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
       });
     }
     __syncwarp();

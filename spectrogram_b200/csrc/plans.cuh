@@ -96,7 +96,7 @@ struct EoPlan {
   const float2* tw2;    // [31][32] pass-2 twiddles of the 1024-point transform (rows 2^u - 1 are the bases)
   const float2* tab;    // [32] W_2048^lane, then [16][32] W_4096^{lane + 32 i}
 };
-int launch_w32eo(int out_kind, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
+int launch_w32eo(int out_kind, int warps, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);
 
 // tu_pcm.cu: PCM ingestion (kernel_pcm.cuh)

@@ -380,9 +380,10 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
   const bool bytes_out = out_kind == SG_OUT_U8 || out_kind == SG_OUT_RGBA8;
   const bool x2_ok = !bytes_out || cfg.min_db >= -300.f;
   int rc;
-  // float dB rows at hop 512 are store-heavy (8 KB per pair): the TMA-staged kernel with 8 warps per SM measured
-  // 556 M frames/s against 526 M on the register-pipelined one (12 warps), so that output takes the branch below
-  const bool db512 = v == 0 && out_kind == SG_OUT_F32_DB && g.hop == 512;
+  // float rows (dB, magnitude) at hop 512 are store-heavy (8 KB per pair): the TMA-staged kernel with 8 warps per SM
+  // measured 556 M frames/s (dB) / 549 M (magnitude) against 526 M / 520 M on the register-pipelined one (12 warps),
+  // so those outputs take the branch below
+  const bool db512 = v == 0 && (out_kind == SG_OUT_F32_DB || out_kind == SG_OUT_F32_MAG) && g.hop == 512;
   if (pl.n_fft == sg::kW32N && (g.hop == 512 || (v == 0 && g.hop == 256)) && (v == 0 || v == 6) && x2_ok && !db512) {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2p(out_kind, v == 6 ? 8 : 12, g, wp, ep, out, e->sm_count, e->device, st);
@@ -397,9 +398,9 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32";
-  } else if (pl.n_fft == sg::kEoN && v == 0 && x2_ok) {
+  } else if (pl.n_fft == sg::kEoN && (v == 0 || v == 6) && x2_ok) {
     const sg::EoPlan eo{pl.win, pl.w32_tw2, pl.eo_tab};
-    rc = sg::launch_w32eo(out_kind, g, eo, ep, out, e->sm_count, e->device, st);
+    rc = sg::launch_w32eo(out_kind, v == 6 ? 12 : 8, g, eo, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "eo4096";
   } else if (pl.n_fft == 400 && v != 1) {
     const sg::R400Plan rp{pl.win, pl.r400_tw, pl.r400_ut};

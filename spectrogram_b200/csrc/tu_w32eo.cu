@@ -15,10 +15,11 @@ static int launch_eo(const FrameGeom& g, const EoPlan& p, const Epilogue& ep, vo
   return (int)cudaGetLastError();
 }
 
-int launch_w32eo(int out_kind, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
+int launch_w32eo(int out_kind, int warps, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st) {
   return dispatch_out(out_kind, [&](auto tag) {
     constexpr int OUT = decltype(tag)::value;
+    if (warps == 12) return launch_eo<OUT, 12>(g, p, ep, out, sm_count, device, st);
     return launch_eo<OUT, kEoWarps>(g, p, ep, out, sm_count, device, st);
   });
 }
