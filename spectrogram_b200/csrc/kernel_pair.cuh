@@ -23,7 +23,9 @@
 
 namespace sg {
 
-constexpr int kPairWarps = 12;
+constexpr int kPairWarps = 12;        // byte outputs; float rows (store-heavy) run 8 warps x 255 registers
+constexpr int kPairWarpsFloat = 8;
+template <int OUT> constexpr int pair_warps() { return (OUT == kOutF32Db || OUT == kOutF32Mag) ? kPairWarpsFloat : kPairWarps; }
 
 template <int LOG2L>
 struct PairShape {
@@ -38,7 +40,7 @@ struct PairShape {
   static constexpr int kWarpBytes = PW * kPairBytes;
   static constexpr int kUtEntries = M / 2 + 2;
   static constexpr int kTableBytes = 16 * L * 16 + LOG2L * 32 * 8 + kUtEntries * 8;   // window quads, bases, W_N^k
-  static constexpr int kSmemBytes = kTableBytes + kPairWarps * kWarpBytes;
+  static constexpr int smem_bytes(int warps) { return kTableBytes + warps * kWarpBytes; }
   static_assert(kTableBytes % 16 == 0 && kPairBytes % 16 == 0, "16-byte alignment of the planes");
 };
 
@@ -57,7 +59,7 @@ __device__ __forceinline__ void dit2_stage_gen_n(C2 (&a)[32], float2 base) {
 }
 
 template <int OUT, int LOG2L, int HOPJ>
-__global__ void __launch_bounds__(kPairWarps * 32, 1)
+__global__ void __launch_bounds__(pair_warps<OUT>() * 32, 1)
 stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
   using S = PairShape<LOG2L>;
@@ -86,7 +88,8 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
 
   // pair geometry of THIS lane group, advanced incrementally
   const int fpc = (int)g.frames_per_clip;
-  const int step = 2 * S::PW * gridDim.x * kPairWarps;   // frames between a lane group's consecutive pairs
+  constexpr int NW = pair_warps<OUT>();
+  const int step = 2 * S::PW * gridDim.x * NW;   // frames between a lane group's consecutive pairs
   const int step_clip = step / fpc, step_t = step - step_clip * fpc;
   const long long d_off = (long long)step_clip * g.clip_stride + (long long)step_t * HOP;
   const long long wrap_off = g.clip_stride - (long long)fpc * HOP;
@@ -99,7 +102,7 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
     t_lo = (int)lo;
     t_hi = (int)hi;
   }
-  long long fa = 2 * S::PW * ((long long)blockIdx.x * kPairWarps + warp) + 2 * h;
+  long long fa = 2 * S::PW * ((long long)blockIdx.x * NW + warp) + 2 * h;
   if (fa - 2 * h >= g.total_frames) return;              // warp-uniform: the warp's first pair has no frame
   int clip = (int)(min(fa, g.total_frames - 1) / fpc);
   int tt = (int)(min(fa, g.total_frames - 1) - (long long)clip * fpc);

@@ -14,12 +14,14 @@ static int launch_one(const FrameGeom& g, const PairPlan& p, const Epilogue& ep,
   constexpr int LOG2L = SG_PAIR_LOG2L;
   using T = typename OutElem<OUT>::type;
   using S = PairShape<LOG2L>;
-  const cudaError_t rc = ensure_dynamic_smem<stft_pair_kernel<OUT, LOG2L, HOPJ>>(S::kSmemBytes, device);
+  constexpr int NW = pair_warps<OUT>();
+  constexpr int smem = S::smem_bytes(NW);
+  const cudaError_t rc = ensure_dynamic_smem<stft_pair_kernel<OUT, LOG2L, HOPJ>>(smem, device);
   if (rc != cudaSuccess) return (int)rc;
   const long long per_warp = 2 * S::PW;                             // frames one warp takes per iteration
   const long long groups = (g.total_frames + per_warp - 1) / per_warp;
-  const int grid = (int)std::min<long long>((groups + kPairWarps - 1) / kPairWarps, sm_count);
-  stft_pair_kernel<OUT, LOG2L, HOPJ><<<grid, kPairWarps * 32, S::kSmemBytes, st>>>(g, p, ep, (T*)out);
+  const int grid = (int)std::min<long long>((groups + NW - 1) / NW, sm_count);
+  stft_pair_kernel<OUT, LOG2L, HOPJ><<<grid, NW * 32, smem, st>>>(g, p, ep, (T*)out);
   return (int)cudaGetLastError();
 }
 
