@@ -165,7 +165,6 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
                       start00 + 5 * 160 + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(span_src) & 15) == 0);
     const bool interior = start >= 0 && start + kR4N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
     const float2* src = reinterpret_cast<const float2*>(x + start) + b;
-    int padstep = 0;                    // extra float2 per 16 elements of j (the per-hop padding of the span layout)
     if (span) {
       const float4* gs = reinterpret_cast<const float4*>(span_src);
       float4* sd = reinterpret_cast<float4*>(tile);
@@ -175,7 +174,6 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
         if (q < 300) sd[q + 3 * ((q * 1639) >> 16)] = __ldg(gs + q);   // + 3 float4 per 40 (one hop)
       }
       src = reinterpret_cast<const float2*>(tile) + 86 * g6 + b;       // (160 + 12) / 2 float2 per hop
-      padstep = 6;
     } else if (!interior) {
       if (start >= 0 && start + kR4N <= g.clip_len) {
         // inside the clip, only misaligned (odd hops): plain copy, eight loads in flight
@@ -193,12 +191,31 @@ stft_r400_kernel(FrameGeom g, R400Plan pl, Epilogue ep, typename OutElem<OUT>::t
     }
     const bool staged = span || __any_sync(0xffffffffu, !interior);
     if (staged) __syncwarp();
+    // the address space is spelled out where it is warp uniform (a pointer that may be shared or global compiles to
+    // generic loads: three L1 wavefronts each instead of two, and the long scoreboard instead of the short one)
     float2 v[40];
-    static_for<0, 40>([&](auto jj) {
-      constexpr int j = decltype(jj)::value;
-      const float2 sv = src[5 * j + (j / 16) * padstep], w = s_win[b + 5 * j];
-      v[j] = make_float2(sv.x * w.x, sv.y * w.y);
-    });
+    if (span) {
+      const unsigned sbase = (unsigned)__cvta_generic_to_shared(src);
+      static_for<0, 40>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        float2 sv;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sv.x), "=f"(sv.y) : "r"(sbase + 8u * (5 * j + (j / 16) * 6)));
+        const float2 w = s_win[b + 5 * j];
+        v[j] = make_float2(sv.x * w.x, sv.y * w.y);
+      });
+    } else if (!staged) {
+      static_for<0, 40>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float2 sv = __ldg(src + 5 * j), w = s_win[b + 5 * j];
+        v[j] = make_float2(sv.x * w.x, sv.y * w.y);
+      });
+    } else {
+      static_for<0, 40>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        const float2 sv = src[5 * j], w = s_win[b + 5 * j];
+        v[j] = make_float2(sv.x * w.x, sv.y * w.y);
+      });
+    }
     if (staged) __syncwarp();   // the staged samples are consumed before the tile is written
 
     // ---- pass 1: 40-point FFT over j, then W_200^{b k1}
