@@ -348,6 +348,29 @@ def run_gpu(args) -> None:
                "d2h_bytes_per_step": int(world * e2e_clips * frames_per_clip * (N_FFT // 2)), "ms_per_step": dt * 1e3,
                "api": "spectrogram_b200.Engine.spectrogram -> sg_stft_batch (pinned host in/out)",
                "host_affinity": affinity}
+        # secondary: the same clips as 16-bit PCM through sg_stft_pcm (ingest on the GPU, 2 bytes per sample over PCIe)
+        if world == 1:
+            from spectrogram_b200 import _lib as L
+            import ctypes as C
+            pin_s16 = sg.PinnedArray((e2e_clips, CLIP_LEN), np.int16)
+            pin_s16.array[...] = np.clip(np.rint(pin_in.array * 32767.0), -32768, 32767).astype(np.int16)
+            cfg_c, _keep = opts.to_c()
+            info = L.PcmInfo(L.PCM_S16, 1, int(SR), CLIP_LEN, 0)
+            lib = L.load()
+
+            def pcm_step():
+                L.check(lib.sg_stft_pcm(eng.handle, pin_s16.array.ctypes.data, e2e_clips, C.byref(info), L.PCM_MONO_MIX,
+                                        C.byref(cfg_c), pin_out.array.ctypes.data))
+            for _ in range(2):
+                pcm_step()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pcm_step()
+            dt16 = (time.perf_counter() - t0) / e2e_steps
+            e2e["pcm16_input"] = {"value": e2e_clips * frames_per_clip / dt16, "unit": "frames/s", "ms_per_step": dt16 * 1e3,
+                                  "h2d_bytes_per_step": int(e2e_clips * CLIP_LEN * 2),
+                                  "api": "sg_stft_pcm (16-bit mono PCM, pinned host in/out)"}
+            pin_s16.free()
         pin_in.free()
         pin_out.free()
 
