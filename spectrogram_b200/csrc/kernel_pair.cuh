@@ -309,21 +309,31 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
         }
       }
     } else {
+      // float rows (dB / magnitude), packed arithmetic, the non-finite rule from the per-frame flag (a poisoned frame
+      // reads 0 / -inf).  A lane's bins are scattered over the row (mirror-pair columns), so the two rows are staged in
+      // the pair's idle planes and leave as 16-byte coalesced stores: direct 4-byte stores fill a quarter of each
+      // 32-byte sector per instruction.
+      float* sfa = reinterpret_cast<float*>(wbase);
+      float* sfb = sfa + M;
+      const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
+      const float z = float_of_poisoned<OUT>();
       static_for<0, 16>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
         int k, mk;
         bins_of(ii, k, mk);
-        {
-          // packed dB / magnitude; the non-finite rule from the per-frame flag (a poisoned frame reads 0 / -inf)
-          const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
-          const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
-          const float z = float_of_poisoned<OUT>();
-          if (alive) {
-            row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
-            if (has_b_out) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
-          }
-        }
+        const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
+        sfa[k] = bad_a ? z : vk.v.x; sfa[mk] = bad_a ? z : vm.v.x;
+        sfb[k] = bad_b ? z : vk.v.y; sfb[mk] = bad_b ? z : vm.v.y;
       });
+      __syncwarp();
+      const uint4* s4 = reinterpret_cast<const uint4*>(sfa);
+      uint4* ra = reinterpret_cast<uint4*>(row_a);
+      uint4* rb = reinterpret_cast<uint4*>(row_b);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {          // M / 4 = 8 L 16-byte words per row
+        if (alive) ra[c * L + t] = s4[c * L + t];
+        if (has_b_out) rb[c * L + t] = s4[M / 4 + c * L + t];
+      }
     }
     __syncwarp();
     if (!__any_sync(0xffffffffu, has_next)) break;   // the lane groups leave together (the exchange barrier is per warp)
