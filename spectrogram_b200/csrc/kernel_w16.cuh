@@ -171,14 +171,20 @@ stft_w16_kernel(FrameGeom g, W16Plan pl, Epilogue ep, typename OutElem<OUT>::typ
       if constexpr (OUT == kOutU8) {
         sb[k] = emit_power_finite<OUT>(pk, ep);
         sb[mk] = emit_power_finite<OUT>(pm, ep);
-      } else if (live) {
-        row[k] = emit_power_finite<OUT>(pk, ep);
-        row[mk] = emit_power_finite<OUT>(pm, ep);
+      } else {
+        // 4-byte rows are staged in the frame's idle tile too: a thread's bins are 16 apart, so direct stores would
+        // fill an eighth of each 32-byte sector per instruction
+        reinterpret_cast<TO*>(A)[k] = emit_power_finite<OUT>(pk, ep);
+        reinterpret_cast<TO*>(A)[mk] = emit_power_finite<OUT>(pm, ep);
       }
     });
+    __syncwarp();
     if constexpr (OUT == kOutU8) {
-      __syncwarp();
       if (live) reinterpret_cast<uint4*>(row)[t] = reinterpret_cast<const uint4*>(sb)[t];
+    } else if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)   // 256 elements = 64 16-byte words, 16 threads
+        reinterpret_cast<uint4*>(row)[c * 16 + t] = reinterpret_cast<const uint4*>(A)[c * 16 + t];
     }
     __syncwarp();
   }
@@ -297,9 +303,9 @@ stft_w16x8_kernel(FrameGeom g, W16Plan pl, Epilogue ep, typename OutElem<OUT>::t
       if constexpr (OUT == kOutU8) {
         sb[k] = emit_power_finite<OUT>(pk, ep);
         sb[mk] = emit_power_finite<OUT>(pm, ep);
-      } else if (live) {
-        row[k] = emit_power_finite<OUT>(pk, ep);
-        row[mk] = emit_power_finite<OUT>(pm, ep);
+      } else {   // 4-byte rows are staged in the frame's idle tile and leave as 16-byte stores
+        reinterpret_cast<TO*>(A)[k] = emit_power_finite<OUT>(pk, ep);
+        reinterpret_cast<TO*>(A)[mk] = emit_power_finite<OUT>(pm, ep);
       }
     };
     auto untangle = [&](float2 zk, float2 zm, int k, float& pk, float& pm) {
@@ -334,9 +340,13 @@ stft_w16x8_kernel(FrameGeom g, W16Plan pl, Epilogue ep, typename OutElem<OUT>::t
       untangle(v[8 + q], zmb, k2, pk, pm);
       emit2(k2, kW8M - k2, pk, pm);
     });
+    __syncwarp();
     if constexpr (OUT == kOutU8) {
-      __syncwarp();
       if (live) reinterpret_cast<uint4*>(row)[t] = reinterpret_cast<const uint4*>(sb)[t];
+    } else if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)   // 128 elements = 32 16-byte words, 8 threads
+        reinterpret_cast<uint4*>(row)[c * 8 + t] = reinterpret_cast<const uint4*>(A)[c * 8 + t];
     }
     __syncwarp();
   }
