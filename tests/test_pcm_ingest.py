@@ -227,3 +227,17 @@ def test_fused_pcm_pipeline_on_one_long_stereo_clip(engine):
     two = engine.spectrogram(planes, opts)
     assert got.shape == (1, 2) + two.shape[1:]
     np.testing.assert_array_equal(got[0], two)
+
+
+@pytest.mark.gpu
+def test_fused_pcm_pipeline_with_smoothing_keeps_one_state_per_plane(engine):
+    """tau > 0: every plane of every clip carries its own recurrence state through the pipeline"""
+    import spectrogram_b200 as sg
+
+    n_clips, frames = 2, 20000
+    raw = random_pcm(po.S16, 2, n_clips * frames, seed=23)
+    opts = sg.Options(fftSize=512, hop=128, smoothingTimeConstant=0.8, output="db")
+    got = engine.spectrogram_pcm(raw, "s16", 2, n_clips=n_clips, mix=False, opts=opts)
+    planes = engine.decode_pcm(raw, "s16", 2, 48000, n_clips=n_clips).planes
+    two = engine.spectrogram(planes.reshape(-1, frames), opts)
+    np.testing.assert_array_equal(got.reshape(two.shape), two)
