@@ -34,7 +34,10 @@ constexpr int kXpPlaneBytes = 2 * 16 * kXpStride * 16;      // re plane + im pla
 constexpr int kXpBytesStage = 2 * kW32M;                    // u8 staging: 1024 (A,B) byte pairs
 constexpr int kXpWarpBytes = kXpPlaneBytes;                 // the byte stage reuses the planes after the exchange
 constexpr int kXpTableBytes = kW32M * 8 + 5 * 32 * 8 + 16 * 32 * 8;   // window + 5 base twiddles + untangle
-constexpr int kXpLoadSteps = 16;   // the next pair's 40 loads are spread over this many untangle steps
+// the next pair's loads are spread over the first kXpLoadSteps of the 16 untangle steps.  Byte rows at hop 512: 16 steps
+// 595, 14: 600, 13: 604, 12: 604, 10: 594, 8: 591 M frames/s; float dB at hop 256 prefers 16 (576 vs 553 M with 13)
+template <int OUT, int HOPJ>
+constexpr int xp_load_steps() { return (HOPJ == 8 && (OUT == kOutU8 || OUT == kOutRgba8)) ? 13 : 16; }
 template <int NW>
 struct XpShape {
   static constexpr int kSmemBytes = kXpTableBytes + NW * kXpWarpBytes;
@@ -105,7 +108,7 @@ template <int OUT, int NW, int HOPJ = 8>   // hop = 64 * HOPJ samples: frame B's
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
-  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ;
+  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ, kLoadSteps = xp_load_steps<OUT, HOPJ>();
   extern __shared__ float4 smem_raw[];
   float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
@@ -281,8 +284,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         pm[0] = P2(lane0 ? p512.v.x : pm[0].v.x, lane0 ? p512.v.y : pm[0].v.y);
       }
       // this step's share of the next pair's loads
-      if constexpr (i < kXpLoadSteps) {
-        static_for<(NLOAD * i) / kXpLoadSteps, (NLOAD * (i + 1)) / kXpLoadSteps>([&](auto mm) {
+      if constexpr (i < kLoadSteps) {
+        static_for<(NLOAD * i) / kLoadSteps, (NLOAD * (i + 1)) / kLoadSteps>([&](auto mm) {
           constexpr int m = decltype(mm)::value;
           s[m] = ldg_nc_f2(nsrc + 32 * m);
         });
