@@ -29,6 +29,23 @@
 
 namespace sg {
 
+// tools/microbench/trace_bench.cu builds this kernel with SG_XP_TRACE: lane 0 of every warp of CTA 0 records clock64 at
+// the phase boundaries of its first kXpTraceIters pairs (the product build compiles the hooks away)
+#ifdef SG_XP_TRACE
+constexpr int kXpTraceIters = 40, kXpTracePoints = 8;
+__device__ long long* g_xp_trace;
+#define XP_TRACE(p)                                                                                              \
+  do {                                                                                                           \
+    if (blockIdx.x == 0 && trace_iter < kXpTraceIters && lane == 0) {                                            \
+      long long t_;                                                                                              \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)::"memory");                                               \
+      g_xp_trace[(warp * kXpTraceIters + trace_iter) * kXpTracePoints + (p)] = t_;                               \
+    }                                                                                                            \
+  } while (0)
+#else
+#define XP_TRACE(p) do {} while (0)
+#endif
+
 constexpr int kXpStride = 33;                               // 16-byte units per row PAIR of one plane
 constexpr int kXpPlaneBytes = 2 * 16 * kXpStride * 16;      // re plane + im plane: 16896 B
 constexpr int kXpBytesStage = 2 * kW32M;                    // u8 staging: 1024 (A,B) byte pairs
@@ -106,7 +123,7 @@ __device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p,
 
 template <int OUT, int NW, int HOPJ = 8>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
-stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
+stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out, int stagger) {
   using T = typename OutElem<OUT>::type;
   constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ, kLoadSteps = xp_load_steps<OUT, HOPJ>();
   extern __shared__ float4 smem_raw[];
@@ -132,6 +149,14 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) s_ut[i] = __ldg(pl.ut + i);
   }
   __syncthreads();
+  // The warps of a CTA start in lock step and every pair costs the same, so without a head start they reach the
+  // exchange (shared-memory bound) and the epilogue (MUFU bound) together and leave the FP32 pipe idle meanwhile.
+  // Warp w waits (w / 4) * stagger + (w % 4) * stagger / 4 cycles once: the three warps of a scheduler (w, w + 4,
+  // w + 8) and the four schedulers of the SM then sit in different phases of the loop.
+  if (stagger > 0) {
+    const long long t0 = clock64(), d = (long long)(warp >> 2) * stagger + (long long)(warp & 3) * (stagger >> 2);
+    while (clock64() - t0 < d) {}
+  }
 
   PairStep st;
   st.fpc = (int)g.frames_per_clip;
@@ -168,7 +193,11 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
   }
 
+#ifdef SG_XP_TRACE
+  int trace_iter = 0;
+#endif
   while (true) {
+    XP_TRACE(0);
     // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
     C2 a[32];
     if (cur_fast) {
@@ -206,6 +235,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     dit2_stage_const<3>(a);
     dit2_stage_const<4>(a);
     dit2_stage_const<5>(a);
+    XP_TRACE(1);
 
     // ---- exchange (32x32 transpose).  Each plane (re, im) keeps rows 2j and 2j+1 interleaved in 16-byte units:
     //      unit (j, col) = [row 2j | row 2j+1].  Lane b stores its element k_a as one 8-byte half (STS.64, the 16
@@ -220,6 +250,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         wim[2 * q] = a[q].im.v;
       });
       asm volatile("bar.sync %0, 32;" ::"r"(warp + 1) : "memory");
+      XP_TRACE(2);
       const float4* rre = xp + lane;
       const float4* rim = rre + 16 * kXpStride;
       static_for<0, 16>([&](auto qq) {   // ascending q0: registers stored last are overwritten last
@@ -231,6 +262,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       });
       __syncwarp();
     }
+    XP_TRACE(3);
 
     // ---- pass 2: stages 6-10, twiddles from the five per-lane bases
     dit2_stage_gen<1>(a, s_twb[0 * 32 + lane]);
@@ -239,6 +271,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     dit2_stage_gen<4>(a, s_twb[3 * 32 + lane]);
     dit2_stage_gen<5>(a, s_twb[4 * 32 + lane]);
     // now a[i] = Z[lane + 32 i] of both frames
+    XP_TRACE(4);
 
     // a non-finite sample makes every Z of its frame non-finite: one test per frame. byte scale -> NaN -> byte 0
     const P2 poison = fma2(a[0].re, bc(0.f), mul2(a[0].im, bc(0.f)));   // 0 or NaN per frame
@@ -291,6 +324,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         });
       }
     });
+    XP_TRACE(5);
     // ---- epilogue
     const bool has_b_out = cur.fa + 1 < g.total_frames;
     T* __restrict__ row_a = out + cur.fa * (long long)kW32M;
@@ -307,8 +341,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
         const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
         if constexpr (OUT == kOutU8) {
-          sb16[k] = (uint16_t)(ka | (kb << 8));
-          sb16[mk] = (uint16_t)(ma | (mb << 8));
+          sb16[k] = (uint16_t)__byte_perm(ka, kb, 0x0040);     // one PRMT instead of SHF + LOP3
+          sb16[mk] = (uint16_t)__byte_perm(ma, mb, 0x0040);
         } else {
           row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
           if (has_b_out) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
@@ -346,6 +380,10 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       });
     }
     __syncwarp();
+    XP_TRACE(6);
+#ifdef SG_XP_TRACE
+    ++trace_iter;
+#endif
     if (!has_next) break;
     cur = nxt;
     cur_fast = nxt_fast;
