@@ -121,7 +121,11 @@ __device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p,
          ((st.pcm_lo + ((unsigned)p.off << 2)) & (align - 1)) == 0;
 }
 
-template <int OUT, int NW, int HOPJ = 8>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
+// ABL (tools/microbench/ablate_bench.cu only; 0 in every product launch) removes one component at a time -- results are
+// wrong, the time saved is that component's marginal cost under the real contention: 1 exchange, 2 mirror shuffles,
+// 4 MUFU/F2IP, 8 next-pair loads, 16 byte stage + row stores, 32 window table reads, 64 lane-0 selects (128: the
+// selects as FSEL instead of PRMT)
+template <int OUT, int NW, int HOPJ = 8, int ABL = 0>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out, int stagger) {
   using T = typename OutElem<OUT>::type;
@@ -183,6 +187,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
   bool cur_fast = pair_is_fast(g, cur, st);
   const int partner = (32 - lane) & 31;
   const bool lane0 = lane == 0;
+  const unsigned lane0_sel = lane0 ? 0x7654u : 0x3210u;   // pick(): lane 0 takes the second operand
 
   float2 s[NLOAD];   // samples of the current pair (fast path): element m = float2 #(lane + 32 m) of the span
   const float2* idle_src = reinterpret_cast<const float2*>(pl.win) + lane;   // 4096 readable floats (build_plan)
@@ -204,7 +209,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       static_for<0, 16>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
-        const float4 w = s_win4[j * 32 + lane];
+        const float4 w = (ABL & 32) ? make_float4(0.3f, 0.4f, 0.5f, 0.6f) : s_win4[j * 32 + lane];
         window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
                       make_float2(w.z, w.w));
       });
@@ -241,7 +246,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     //      unit (j, col) = [row 2j | row 2j+1].  Lane b stores its element k_a as one 8-byte half (STS.64, the 16
     //      lanes of a half-warp fill 8 whole units: conflict free); lane a then reads column a of a row pair with
     //      one LDS.128 -- rows b = 2j, 2j+1 hold q = bitrev4(j), bitrev4(j) + 16.
-    {
+    if constexpr (!(ABL & 1)) {
       float2* wre = reinterpret_cast<float2*>(xp) + ((lane >> 1) * kXpStride) * 2 + (lane & 1);
       float2* wim = wre + 16 * kXpStride * 2;
       static_for<0, 32>([&](auto qq) {
@@ -291,12 +296,28 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     static_for<0, 16>([&](auto ii) {
       constexpr int i = 15 - decltype(ii)::value;
       constexpr int src = 31 - i, own = (32 - i) & 31;
-      const float mra = __shfl_sync(0xffffffffu, a[src].re.v.x, partner);
-      const float mrb = __shfl_sync(0xffffffffu, a[src].re.v.y, partner);
-      const float mia = __shfl_sync(0xffffffffu, a[src].im.v.x, partner);
-      const float mib = __shfl_sync(0xffffffffu, a[src].im.v.y, partner);
-      a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
-      a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
+      float mra = a[src].re.v.x, mrb = a[src].re.v.y, mia = a[src].im.v.x, mib = a[src].im.v.y;
+      if constexpr (!(ABL & 2)) {
+        mra = __shfl_sync(0xffffffffu, mra, partner);
+        mrb = __shfl_sync(0xffffffffu, mrb, partner);
+        mia = __shfl_sync(0xffffffffu, mia, partner);
+        mib = __shfl_sync(0xffffffffu, mib, partner);
+      }
+      if constexpr (ABL & 64) {
+        a[src].re = P2(mra, mrb);
+        a[src].im = P2(mia, mib);
+      } else {
+        // lane 0 keeps its own value.  A byte permute with a per-lane selector, not a float select: FSEL competes with
+        // FFMA2 for issue (tools/microbench/xu_bench.cu: FSEL + FFMA2 4.0 cycles per pair of instructions, PRMT + FFMA2
+        // 2.35); the 64 selects cost the kernel 6.7 % as FSELs (ablate_bench.cu)
+        if constexpr (ABL & 128) {   // the FSEL form, for the A/B
+          a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
+          a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
+        } else {
+          a[src].re = P2(pick(mra, a[own].re.v.x, lane0_sel), pick(mrb, a[own].re.v.y, lane0_sel));
+          a[src].im = P2(pick(mia, a[own].im.v.x, lane0_sel), pick(mib, a[own].im.v.y, lane0_sel));
+        }
+      }
     });
     P2 pk[16], pm[16];
     static_for<0, 16>([&](auto ii) {
@@ -314,10 +335,10 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       pm[i] = fma2(yr, yr, mul2(yi, yi));
       if constexpr (i == 0) {
         // lane 0: the mirror of k = 0 is the Nyquist bin (dropped); its slot carries bin 512
-        pm[0] = P2(lane0 ? p512.v.x : pm[0].v.x, lane0 ? p512.v.y : pm[0].v.y);
+        pm[0] = P2(pick(pm[0].v.x, p512.v.x, lane0_sel), pick(pm[0].v.y, p512.v.y, lane0_sel));
       }
       // this step's share of the next pair's loads
-      if constexpr (i < kLoadSteps) {
+      if constexpr (i < kLoadSteps && !(ABL & 8)) {
         static_for<(NLOAD * i) / kLoadSteps, (NLOAD * (i + 1)) / kLoadSteps>([&](auto mm) {
           constexpr int m = decltype(mm)::value;
           s[m] = ldg_nc_f2(nsrc + 32 * m);
@@ -336,11 +357,13 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         const int k = lane + 32 * i;
         int mk = kW32M - k;
         if constexpr (i == 0) { if (lane0) mk = 512; }
-        const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), scale, bc(ep.byte_b));
-        const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), scale, bc(ep.byte_b));
-        const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
-        const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
-        if constexpr (OUT == kOutU8) {
+        const P2 vk = fma2((ABL & 4) ? pk[i] : P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), scale, bc(ep.byte_b));
+        const P2 vm = fma2((ABL & 4) ? pm[i] : P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), scale, bc(ep.byte_b));
+        const unsigned ka = (ABL & 4) ? __float_as_uint(vk.v.x) : byte_of_scaled(vk.v.x), kb = (ABL & 4) ? __float_as_uint(vk.v.y) : byte_of_scaled(vk.v.y);
+        const unsigned ma = (ABL & 4) ? __float_as_uint(vm.v.x) : byte_of_scaled(vm.v.x), mb = (ABL & 4) ? __float_as_uint(vm.v.y) : byte_of_scaled(vm.v.y);
+        if constexpr (ABL & 16) {
+          if (((ka ^ kb) + (ma ^ mb)) == 0x12345678u) row_a[k] = (T)ka;   // keeps the values live, never stores
+        } else if constexpr (OUT == kOutU8) {
           sb16[k] = (uint16_t)__byte_perm(ka, kb, 0x0040);     // one PRMT instead of SHF + LOP3
           sb16[mk] = (uint16_t)__byte_perm(ma, mb, 0x0040);
         } else {
@@ -348,7 +371,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
           if (has_b_out) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
         }
       });
-      if constexpr (OUT == kOutU8) {
+      if constexpr (OUT == kOutU8 && !(ABL & 16)) {
         __syncwarp();
         // de-interleave the (A,B) byte pairs: 8 bins per lane per round, 8-byte coalesced row stores
         const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
@@ -367,7 +390,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       // powers below 2^-126 read as 0.
       // (Measured slower, 510-511 vs 529 M frames/s in dB: a warp-uniform branch around a select-free copy of this loop,
       //  and select-free stores followed by a cold loop that overwrites a poisoned frame's rows.)
-      const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
+      const unsigned bad_a = poison.v.x == 0.f ? 0x3210u : 0x7654u, bad_b = poison.v.y == 0.f ? 0x3210u : 0x7654u;
       const float z = float_of_poisoned<OUT>();
       static_for<0, 16>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -375,8 +398,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         int mk = kW32M - k;
         if constexpr (i == 0) { if (lane0) mk = 512; }
         const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
-        row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
-        if (has_b_out) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
+        row_a[k] = pick(vk.v.x, z, bad_a); row_a[mk] = pick(vm.v.x, z, bad_a);
+        if (has_b_out) { row_b[k] = pick(vk.v.y, z, bad_b); row_b[mk] = pick(vm.v.y, z, bad_b); }
       });
     }
     __syncwarp();
