@@ -80,7 +80,8 @@ print("ok", rank)
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--clips-per-gpu", "8"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     import json
@@ -88,3 +89,4 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "stft_frames_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["n_fft"] == 2048
+    assert line["config"]["clips_per_gpu"] == 8      # the CPU arm runs the GPU arm's batch, clip for clip
