@@ -447,6 +447,7 @@ def run_gpu(args) -> None:
     barrier()
     ms_local = ev0.elapsed_time(ev1) / args.steps
     launches = eng.launch_count - launches0
+    headline_kernel = eng.last_kernel
     clocks = sampler.stop()
     ms = max_over_ranks(ms_local, dev)
     total_frames = sum_over_ranks(frames, dev)
@@ -585,7 +586,7 @@ def run_gpu(args) -> None:
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "audio_s_per_s": value * HOP / SR,
             "config": workload_config(clips),
-            "kernel": eng.last_kernel,
+            "kernel": headline_kernel,
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -112,7 +112,6 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
   };
   bool cur_fast = is_fast(fa, tt, off);
   const bool c0 = t == 0;
-  const unsigned c0_sel = c0 ? 0x7654u : 0x3210u;   // pick(): the group's thread 0 takes the second operand
   // mirror pair r of this lane: columns (ka, kb) = (t + L r, 32 - (t + L r)); lane 0's pair 0 is (0, 16)
   int cols[NCOL];
   static_for<0, NP>([&](auto rr) {
@@ -232,10 +231,10 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
     static_for<0, L / 2>([&](auto qq) {
       constexpr int q = L / 2 - 1 - decltype(qq)::value;
       const C2 na = a[q ? L - q : 0], nb = a[2 * L - 1 - q];
-      a[2 * L - 1 - q].re = P2(pick(a[2 * L - 1 - q].re.v.x, na.re.v.x, c0_sel), pick(a[2 * L - 1 - q].re.v.y, na.re.v.y, c0_sel));
-      a[2 * L - 1 - q].im = P2(pick(a[2 * L - 1 - q].im.v.x, na.im.v.x, c0_sel), pick(a[2 * L - 1 - q].im.v.y, na.im.v.y, c0_sel));
-      a[L - 1 - q].re = P2(pick(a[L - 1 - q].re.v.x, nb.re.v.x, c0_sel), pick(a[L - 1 - q].re.v.y, nb.re.v.y, c0_sel));
-      a[L - 1 - q].im = P2(pick(a[L - 1 - q].im.v.x, nb.im.v.x, c0_sel), pick(a[L - 1 - q].im.v.y, nb.im.v.y, c0_sel));
+      a[2 * L - 1 - q].re = P2(c0 ? na.re.v.x : a[2 * L - 1 - q].re.v.x, c0 ? na.re.v.y : a[2 * L - 1 - q].re.v.y);
+      a[2 * L - 1 - q].im = P2(c0 ? na.im.v.x : a[2 * L - 1 - q].im.v.x, c0 ? na.im.v.y : a[2 * L - 1 - q].im.v.y);
+      a[L - 1 - q].re = P2(c0 ? nb.re.v.x : a[L - 1 - q].re.v.x, c0 ? nb.re.v.y : a[L - 1 - q].re.v.y);
+      a[L - 1 - q].im = P2(c0 ? nb.im.v.x : a[L - 1 - q].im.v.x, c0 ? nb.im.v.y : a[L - 1 - q].im.v.y);
     });
     P2 pk[16], pm[16];   // slot i = (r * L/2 + q) * 2 + {0: column ka, 1: column kb}
     static_for<0, NP>([&](auto rr) {
@@ -258,7 +257,7 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
         };
         pair(a[oa + q], a[ob + L - 1 - q], ka + 32 * q, pk[slot], pm[slot]);
         pair(a[ob + q], a[oa + L - 1 - q], kb + 32 * q, pk[slot + 1], pm[slot + 1]);
-        if constexpr (slot == 0) pm[0] = P2(pick(pm[0].v.x, pmid.v.x, c0_sel), pick(pm[0].v.y, pmid.v.y, c0_sel));
+        if constexpr (slot == 0) pm[0] = P2(c0 ? pmid.v.x : pm[0].v.x, c0 ? pmid.v.y : pm[0].v.y);
         // this step's share of the next pair's loads
         constexpr int stepi = r * (L / 2) + q;
         static_for<(NLOAD * stepi) / 8, (NLOAD * (stepi + 1)) / 8>([&](auto mm) {
@@ -316,15 +315,15 @@ stft_pair_kernel(FrameGeom g, PairPlan pl, Epilogue ep, typename OutElem<OUT>::t
       // 32-byte sector per instruction.
       float* sfa = reinterpret_cast<float*>(wbase);
       float* sfb = sfa + M;
-      const unsigned bad_a = poison.v.x == 0.f ? 0x3210u : 0x7654u, bad_b = poison.v.y == 0.f ? 0x3210u : 0x7654u;
+      const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
       const float z = float_of_poisoned<OUT>();
       static_for<0, 16>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
         int k, mk;
         bins_of(ii, k, mk);
         const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
-        sfa[k] = pick(vk.v.x, z, bad_a); sfa[mk] = pick(vm.v.x, z, bad_a);
-        sfb[k] = pick(vk.v.y, z, bad_b); sfb[mk] = pick(vm.v.y, z, bad_b);
+        sfa[k] = bad_a ? z : vk.v.x; sfa[mk] = bad_a ? z : vm.v.x;
+        sfb[k] = bad_b ? z : vk.v.y; sfb[mk] = bad_b ? z : vm.v.y;
       });
       __syncwarp();
       const uint4* s4 = reinterpret_cast<const uint4*>(sfa);

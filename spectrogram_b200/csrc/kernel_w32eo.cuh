@@ -78,7 +78,6 @@ stft_w32eo_kernel(FrameGeom g, EoPlan pl, Epilogue ep, typename OutElem<OUT>::ty
 
   const int partner = (32 - lane) & 31;
   const bool lane0 = lane == 0;
-  const unsigned lane0_sel = lane0 ? 0x7654u : 0x3210u;   // pick(): lane 0 takes the second operand
   const long long fstep = (long long)gridDim.x * NW;
   const bool base_aligned = (reinterpret_cast<uintptr_t>(g.pcm) & 15) == 0;
 
@@ -211,8 +210,8 @@ stft_w32eo_kernel(FrameGeom g, EoPlan pl, Epilogue ep, typename OutElem<OUT>::ty
       const float mrb = __shfl_sync(0xffffffffu, a[src].re.v.y, partner);
       const float mia = __shfl_sync(0xffffffffu, a[src].im.v.x, partner);
       const float mib = __shfl_sync(0xffffffffu, a[src].im.v.y, partner);
-      a[src].re = P2(pick(mra, a[own].re.v.x, lane0_sel), pick(mrb, a[own].re.v.y, lane0_sel));   // PRMT, not FSEL
-      a[src].im = P2(pick(mia, a[own].im.v.x, lane0_sel), pick(mib, a[own].im.v.y, lane0_sel));
+      a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
+      a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
     });
     P2 pk[16], pm[16];   // pk[i] = |2X|^2 at (k', k' + 1024);  pm[i] at (2048 - k', 1024 - k')
     static_for<0, 16>([&](auto ii) {
@@ -223,7 +222,7 @@ stft_w32eo_kernel(FrameGeom g, EoPlan pl, Epilogue ep, typename OutElem<OUT>::ty
       if constexpr (i == 0) {
         // lane 0: the mirrors of k' = 0 are the Nyquist bin (dropped) and bin 1024 again; the slot carries bins
         // 512 / 1536 (stored like every mirror slot: lower half -> upper row)
-        pm[0] = P2(pick(pm[0].v.x, p512.v.y, lane0_sel), pick(pm[0].v.y, p512.v.x, lane0_sel));
+        pm[0] = P2(lane0 ? p512.v.y : pm[0].v.x, lane0 ? p512.v.x : pm[0].v.y);
       }
       s[i] = ldg_nc_f4(nsrc + 32 * elem_of(i));
     });

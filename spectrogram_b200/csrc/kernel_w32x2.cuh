@@ -95,13 +95,6 @@ __device__ __forceinline__ void dit2_stage_table(C2 (&a)[32], const float2* __re
   });
 }
 
-// A select that issues on the integer pipe (PRMT with a per-lane selector register): sel = 0x3210 gives x, 0x7654 gives y.
-// FSEL competes with FFMA2 for issue (tools/microbench/xu_bench.cu: FSEL + FFMA2 4.0 cycles per instruction pair per
-// scheduler, PRMT + FFMA2 2.35); the headline kernel's 64 lane-0 selects cost it 6.7 % as FSELs (ablate_bench.cu).
-__device__ __forceinline__ float pick(float x, float y, unsigned sel) {
-  return __uint_as_float(__byte_perm(__float_as_uint(x), __float_as_uint(y), sel));
-}
-
 // ---------------------------------------------------------------- epilogue helpers
 // float dB of one power pair: db_scale * lg2(p) + db_off, packed (lg2.approx.ftz: powers below 2^-126 read as 0)
 __device__ __forceinline__ P2 db_of_power(P2 p, const Epilogue& ep) {
@@ -318,7 +311,7 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
     // now a[i] = Z[lane + 32 i] of both frames
     // a non-finite sample makes every Z of its frame non-finite: one flag per frame for the float dB path
     const P2 poison = fma2(a[0].re, bc(0.f), mul2(a[0].im, bc(0.f)));   // 0 or NaN per frame
-    const unsigned bad_a = poison.v.x == 0.f ? 0x3210u : 0x7654u, bad_b = poison.v.y == 0.f ? 0x3210u : 0x7654u;
+    const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
     const P2 byte_scale = add2(bc(ep.byte_a), poison);
 
     // ---- untangle exchange: upper half (k >= 512) to smem at index k - 512; Z[1024] == Z[0] at 512.
@@ -380,8 +373,8 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
         // float dB / magnitude, packed; the non-finite rule from the per-frame flag (magnitude 0: -inf dB)
         const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
         const float z = float_of_poisoned<OUT>();
-        row_a[k] = pick(vk.v.x, z, bad_a); row_a[mk] = pick(vm.v.x, z, bad_a);
-        if (cur.has_b) { row_b[k] = pick(vk.v.y, z, bad_b); row_b[mk] = pick(vm.v.y, z, bad_b); }
+        row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
+        if (cur.has_b) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
       }
     });
     if constexpr (OUT == kOutU8) {

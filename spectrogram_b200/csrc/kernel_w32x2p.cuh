@@ -89,6 +89,11 @@ __device__ __forceinline__ void dit2_stage_gen(C2 (&a)[32], float2 base) {
   });
 }
 
+// sel = 0x3210: x, sel = 0x7654: y -- a select as PRMT with a per-lane selector (the ABL 128 experiment only: FSEL is faster)
+__device__ __forceinline__ float pick(float x, float y, unsigned sel) {
+  return __uint_as_float(__byte_perm(__float_as_uint(x), __float_as_uint(y), sel));
+}
+
 // volatile: the loads stay where they are written (interleaved with the untangle)
 __device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
   float2 v;
@@ -124,7 +129,7 @@ __device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p,
 // ABL (tools/microbench/ablate_bench.cu only; 0 in every product launch) removes one component at a time -- results are
 // wrong, the time saved is that component's marginal cost under the real contention: 1 exchange, 2 mirror shuffles,
 // 4 MUFU/F2IP, 8 next-pair loads, 16 byte stage + row stores, 32 window table reads, 64 lane-0 selects (128: the
-// selects as FSEL instead of PRMT)
+// selects as PRMT instead of FSEL)
 template <int OUT, int NW, int HOPJ = 8, int ABL = 0>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out, int stagger) {
@@ -307,15 +312,13 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         a[src].re = P2(mra, mrb);
         a[src].im = P2(mia, mib);
       } else {
-        // lane 0 keeps its own value.  A byte permute with a per-lane selector, not a float select: FSEL competes with
-        // FFMA2 for issue (tools/microbench/xu_bench.cu: FSEL + FFMA2 4.0 cycles per pair of instructions, PRMT + FFMA2
-        // 2.35); the 64 selects cost the kernel 6.7 % as FSELs (ablate_bench.cu)
-        if constexpr (ABL & 128) {   // the FSEL form, for the A/B
-          a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
-          a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
-        } else {
+        // lane 0 keeps its own value: 64 FSELs, 6.7 % of the kernel's time (ablate_bench.cu)
+        if constexpr (ABL & 128) {   // the selects as PRMT with a per-lane selector: measured 580 vs 607 M frames/s
           a[src].re = P2(pick(mra, a[own].re.v.x, lane0_sel), pick(mrb, a[own].re.v.y, lane0_sel));
           a[src].im = P2(pick(mia, a[own].im.v.x, lane0_sel), pick(mib, a[own].im.v.y, lane0_sel));
+        } else {
+          a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
+          a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
         }
       }
     });
@@ -335,7 +338,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       pm[i] = fma2(yr, yr, mul2(yi, yi));
       if constexpr (i == 0) {
         // lane 0: the mirror of k = 0 is the Nyquist bin (dropped); its slot carries bin 512
-        pm[0] = P2(pick(pm[0].v.x, p512.v.x, lane0_sel), pick(pm[0].v.y, p512.v.y, lane0_sel));
+        pm[0] = P2(lane0 ? p512.v.x : pm[0].v.x, lane0 ? p512.v.y : pm[0].v.y);
       }
       // this step's share of the next pair's loads
       if constexpr (i < kLoadSteps && !(ABL & 8)) {
@@ -390,7 +393,7 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
       // powers below 2^-126 read as 0.
       // (Measured slower, 510-511 vs 529 M frames/s in dB: a warp-uniform branch around a select-free copy of this loop,
       //  and select-free stores followed by a cold loop that overwrites a poisoned frame's rows.)
-      const unsigned bad_a = poison.v.x == 0.f ? 0x3210u : 0x7654u, bad_b = poison.v.y == 0.f ? 0x3210u : 0x7654u;
+      const bool bad_a = !(poison.v.x == 0.f), bad_b = !(poison.v.y == 0.f);
       const float z = float_of_poisoned<OUT>();
       static_for<0, 16>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -398,8 +401,8 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         int mk = kW32M - k;
         if constexpr (i == 0) { if (lane0) mk = 512; }
         const P2 vk = float_of_power<OUT>(pk[i], ep), vm = float_of_power<OUT>(pm[i], ep);
-        row_a[k] = pick(vk.v.x, z, bad_a); row_a[mk] = pick(vm.v.x, z, bad_a);
-        if (has_b_out) { row_b[k] = pick(vk.v.y, z, bad_b); row_b[mk] = pick(vm.v.y, z, bad_b); }
+        row_a[k] = bad_a ? z : vk.v.x; row_a[mk] = bad_a ? z : vm.v.x;
+        if (has_b_out) { row_b[k] = bad_b ? z : vk.v.y; row_b[mk] = bad_b ? z : vm.v.y; }
       });
     }
     __syncwarp();
