@@ -336,10 +336,11 @@ struct sg_engine {
   std::map<PlanKey, Plan> plans;
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
-  DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
+  DevBuf scratch_mag, scratch_state, scratch_carry, scan_flags, d_in, d_out;
   DevBuf d_raw[2];                   // interleaved PCM bytes in flight (sg_stft_pcm)
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
+  unsigned scan_epoch = 0;           // smooth_scan_kernel: a launch's `done` words take this value
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   const char* last_kernel = "none";
   std::mutex mu;
@@ -453,21 +454,27 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
   using T = typename sg::OutElem<OUT>::type;
   const long long n = n_clips * bins;
   if (n <= 0 || frames <= 0) return SG_OK;
-  // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run
+  // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run (one kernel:
+  // aggregates, decoupled look-back, emit)
   const long long want_threads = 2048LL * e->sm_count;
   if (n < want_threads && frames >= 256) {
     const int chunk = (int)std::max<long long>(32, std::min<long long>(1024, frames * n / want_threads));
     const long long n_chunks = (frames + chunk - 1) / chunk;
-    SG_TRY(e->scratch_carry.reserve((size_t)n * n_chunks * sizeof(float)));
-    float* carry = (float*)e->scratch_carry.p;
-    const long long nt = n * n_chunks;
-    sg::scan_chunk_sums_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, carry, n_clips, frames, bins, chunk,
-                                                                           n_chunks, tau);
-    sg::scan_chunk_carry_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(carry, state, n_clips, frames, bins, chunk,
-                                                                            n_chunks, tau);
-    sg::scan_chunk_emit_kernel<OUT><<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mags, (T*)out, carry, state, n_clips,
-                                                                                frames, bins, chunk, n_chunks, tau, ep);
-    e->launches += 3;
+    const long long nt = n * n_chunks, blocks = (nt + 255) / 256;
+    SG_TRY(e->scratch_carry.reserve((size_t)nt * sizeof(float)));
+    // the flag words live in a buffer of their own: it only ever holds epochs of earlier launches (or zeros)
+    const size_t words = (size_t)blocks + 1;
+    if (words * sizeof(unsigned) > e->scan_flags.cap) {
+      SG_TRY(e->scan_flags.reserve(std::max<size_t>(2 * words, 4096) * sizeof(unsigned)));
+      SG_CUDA(cudaMemsetAsync(e->scan_flags.p, 0, e->scan_flags.cap, st));
+    }
+    float* agg = (float*)e->scratch_carry.p;
+    unsigned* ticket = (unsigned*)e->scan_flags.p;
+    unsigned* done = ticket + 1;
+    SG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    sg::ScanGeom sgm{n_clips, frames, n_chunks, bins, chunk, tau, std::pow(tau, (double)chunk), ++e->scan_epoch};
+    sg::smooth_scan_kernel<OUT><<<(unsigned)blocks, 256, 0, st>>>(mags, (T*)out, state, agg, done, ticket, sgm, ep);
+    e->launches++;
     SG_CUDA(cudaGetLastError());
     return SG_OK;
   }
@@ -510,27 +517,38 @@ int run_range(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const flo
     }
     return SG_OK;
   }
-  // tau > 0: bound the scratch, walk clip groups
-  const size_t per_clip = (size_t)nframes * bins * sizeof(float);
-  const long long group = std::max<long long>(1, std::min<long long>(n_clips, (long long)((1ull << 30) / std::max<size_t>(per_clip, 1))));
-  SG_TRY(e->scratch_mag.reserve((size_t)group * per_clip));
+  // tau > 0 on a shape without a fused kernel: frame kernel -> linear magnitudes -> recurrence kernel, in tiles small
+  // enough for the magnitudes to stay in L2 between the two kernels (they are written and read once and the tile
+  // buffer is reused, so they never reach HBM: DRAM traffic stays at the algorithmic bytes).  A tile is a group of
+  // whole clips, or a frame range of one clip chained through `state`.
+  const size_t kTileBytes = 40u << 20;
+  const size_t frame_bytes = (size_t)bins * sizeof(float);
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * cfg.n_fft, lut);
-  for (long long c0 = 0; c0 < n_clips; c0 += group) {
-    const long long nc = std::min(group, n_clips - c0);
-    sg::FrameGeom g{pcm_dev + c0 * clip_stride, clip_len, clip_stride, nframes, nc * nframes, start0, cfg.n_fft, cfg.hop};
-    SG_TRY(launch_frames(e, pl, g, cfg, SG_OUT_F32_MAG, lut, e->scratch_mag.p, st));
-    if (nframes == frames_total) {
+  const long long tile_frames = std::max<long long>(1, (long long)(kTileBytes / frame_bytes));
+  if (nframes <= tile_frames && nframes == frames_total) {
+    const long long group = std::max<long long>(1, std::min<long long>(n_clips, tile_frames / nframes));
+    SG_TRY(e->scratch_mag.reserve((size_t)group * nframes * frame_bytes));
+    for (long long c0 = 0; c0 < n_clips; c0 += group) {
+      const long long nc = std::min(group, n_clips - c0);
+      sg::FrameGeom g{pcm_dev + c0 * clip_stride, clip_len, clip_stride, nframes, nc * nframes, start0, cfg.n_fft, cfg.hop};
+      SG_TRY(launch_frames(e, pl, g, cfg, SG_OUT_F32_MAG, lut, e->scratch_mag.p, st));
       char* o = (char*)out_dev + (size_t)c0 * frames_total * bins * eb;
       SG_TRY(launch_smooth(e, cfg.output, (const float*)e->scratch_mag.p, o, state + c0 * bins, nc, nframes, bins,
                            cfg.smoothing, ep, st));
-    } else {
-      for (long long c = 0; c < nc; ++c) {
-        char* o = (char*)out_dev + ((size_t)(c0 + c) * frames_total + t0) * bins * eb;
-        SG_TRY(launch_smooth(e, cfg.output, (const float*)e->scratch_mag.p + (size_t)c * nframes * bins, o,
-                             state + (c0 + c) * bins, 1, nframes, bins, cfg.smoothing, ep, st));
-      }
     }
+    return SG_OK;
   }
+  // long clips (or a frame range of several clips): clip by clip, frame tiles chained through the state
+  SG_TRY(e->scratch_mag.reserve((size_t)std::min(nframes, tile_frames) * frame_bytes));
+  for (long long c = 0; c < n_clips; ++c)
+    for (long long tt = 0; tt < nframes; tt += tile_frames) {
+      const long long nt = std::min(tile_frames, nframes - tt);
+      sg::FrameGeom g{pcm_dev + c * clip_stride, clip_len, clip_stride, nt, nt, start0 + tt * cfg.hop, cfg.n_fft, cfg.hop};
+      SG_TRY(launch_frames(e, pl, g, cfg, SG_OUT_F32_MAG, lut, e->scratch_mag.p, st));
+      char* o = (char*)out_dev + ((size_t)c * frames_total + t0 + tt) * bins * eb;
+      SG_TRY(launch_smooth(e, cfg.output, (const float*)e->scratch_mag.p, o, state + c * bins, 1, nt, bins, cfg.smoothing,
+                           ep, st));
+    }
   return SG_OK;
 }
 
@@ -609,7 +627,7 @@ int sg_engine_destroy(sg_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
-  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->d_in.release(); e->d_out.release();
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->scan_flags.release(); e->d_in.release(); e->d_out.release();
   e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);

@@ -524,3 +524,23 @@ def test_non_finite_samples_zero_their_frames_only(engine, n_fft, hop, bad_value
             assert np.all(np.isneginf(got[1][hit]))
         else:
             assert not got[1][hit].any()
+
+
+def test_time_parallel_scan_agrees_with_the_sequential_recurrence(engine):
+    """tau > 0: one long clip takes the chunked look-back scan (aggregates carried as float), a large batch takes one
+    thread per (clip, bin) walking the frames in order.  Same clip both ways: the smoothed magnitudes agree to float
+    rounding of the carried state, the bytes to the LSB."""
+    rng = np.random.default_rng(99)
+    n_fft, hop, frames = 256, 64, 320
+    clip_len = n_fft + (frames - 1) * hop
+    one = (0.2 * rng.standard_normal(clip_len)).astype(np.float32)
+    batch = np.broadcast_to(one, (2400, clip_len)).copy()      # 2400 x 128 bins > 2048 threads x 148 SMs: sequential kernel
+    for out in ("mag", "u8"):
+        opts = sg.Options(fftSize=n_fft, hop=hop, output=out, smoothingTimeConstant=0.9)
+        a = engine.spectrogram(one, opts)
+        b = engine.spectrogram(batch, opts)[17]
+        if out == "mag":
+            assert np.max(np.abs(a - b) / (np.abs(b) + 1e-30)) < 2e-6
+        else:
+            d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+            assert d.max() <= 1 and (d != 0).mean() < 1e-4
