@@ -2,6 +2,8 @@
 // step 4, 3D/visualizer.js:351,357,362 set tau per mode), the byte -> colour LUT
 // (bin/shaders/sonogram-*.shader) and the byte time-domain getter (3D/visualizer.js:363).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace sg {
@@ -43,98 +45,108 @@ smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
 }
 
 // ---- time-parallel form of the same recurrence for long clips with few (clip, bin) pairs, ONE kernel ---------------
-// The recurrence is linear with a constant coefficient, so a clip's frames are cut into chunks of `chunk` frames and
-// a thread owns one (chunk, clip, bin):
-//   (1) the chunk's zero-state response at its last frame (its "aggregate") is published,
-//   (2) the true state at the chunk's start is the decayed sum of the aggregates of the chunks before it (decoupled
-//       look-back: every aggregate is produced concurrently, nobody waits for a predecessor's FINAL value),
-//   (3) the chunk is re-run from that state, emitting dB / bytes (the magnitudes are still in L1/L2).
-// Blocks take their index from an atomic ticket, so a block only ever waits for blocks that started before it.
+// The recurrence is linear with a constant coefficient, so a clip's frames are cut into chunks of `chunk` frames:
+//   (A) each chunk's zero-state response at its last frame (thread per (clip, chunk, bin), bins coalesced),
+//   (B) the same recurrence one level up (s' = dec * s + local) turns those into the true state at every chunk start:
+//       one warp per (clip, bin) scans 32 chunks at a time with a shuffle prefix scan of decayed sums, so a
+//       45 000-frame clip needs ~45 warp steps instead of ~1400 sequential ones,
+//   (C) the chunks re-run in parallel from their true initial state, emitting dB / bytes (the magnitudes are still
+//       in L1/L2).
+// The three phases are grid-stride loops of one cooperative launch separated by grid barriers (the grid is sized to
+// be co-resident), so a two-channel clip costs one launch after its frame kernel instead of three.
 // Inputs are finite (the frame kernels map non-finite magnitudes to 0), so the [SPEC] non-finite rule cannot fire
-// inside the sums; step (3) still applies it per frame like the sequential kernel.  The carried state differs from
-// the sequential kernel's by float rounding of the aggregates (a few ulp): tests/test_gpu_parity.py compares the two.
+// inside the sums; phase (C) still applies it per frame like the sequential kernel.  The carried state differs from
+// the sequential kernel's by float rounding of the chunk sums (a few ulp): tests/test_gpu_parity.py compares the two.
+// carry: [n_clips][bins][n_chunks] float (chunk fastest: phase B reads a bin's chunks coalesced).
 struct ScanGeom {
   long long n_clips, frames, n_chunks;
   int bins, chunk;
-  double tau, dec;        // dec = tau^chunk
-  unsigned epoch;         // value a block's `done` word takes when its aggregates are visible
+  double tau;
 };
 
 template <int OUT>
 __global__ void __launch_bounds__(256)
 smooth_scan_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* __restrict__ out,
-                   float* __restrict__ state, float* __restrict__ agg, unsigned* __restrict__ done,
-                   unsigned* __restrict__ ticket, ScanGeom sg_, Epilogue ep) {
-  __shared__ unsigned s_bid;
-  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const unsigned bid = s_bid;
-  const long long per_chunk = sg_.n_clips * sg_.bins;             // threads per chunk index
-  const long long flat = (long long)bid * blockDim.x + threadIdx.x;
-  const bool live = flat < per_chunk * sg_.n_chunks;
-  long long j = 0, clip = 0;
-  int b = 0;
-  const float* __restrict__ m = mags;
-  long long t0 = 0, t1 = 0;
-  const double k1 = 1.0 - sg_.tau;
-  if (live) {
-    j = flat / per_chunk;
-    const long long r = flat - j * per_chunk;
-    clip = r / sg_.bins;
-    b = (int)(r - clip * sg_.bins);
-    m = mags + clip * sg_.frames * sg_.bins + b;
-    t0 = j * sg_.chunk;
-    t1 = min(sg_.frames, t0 + (long long)sg_.chunk);
-    // (1) zero-state response; the loads do not depend on the recurrence: eight in flight per thread
-    if (j + 1 < sg_.n_chunks) {          // the last chunk is nobody's predecessor
-      double s = 0.0;
-      long long t = t0;
-      for (; t + 8 <= t1; t += 8) {
-        float v[8];
+                   float* __restrict__ state, float* __restrict__ carry, ScanGeom sg_, Epilogue ep) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const long long n_clips = sg_.n_clips, frames = sg_.frames, n_chunks = sg_.n_chunks;
+  const int bins = sg_.bins, chunk = sg_.chunk;
+  const double tau = sg_.tau, k1 = 1.0 - tau;
+  const long long nthreads = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_clips * n_chunks * bins;
+  // ---- (A)
+  for (long long idx = tid; idx < total; idx += nthreads) {
+    const int b = (int)(idx % bins);
+    const long long cj = idx / bins, clip = cj / n_chunks, j = cj - clip * n_chunks;
+    if (j + 1 == n_chunks) continue;          // the last chunk is nobody's predecessor
+    const long long t0 = j * chunk, t1 = min(frames, t0 + (long long)chunk);
+    const float* __restrict__ m = mags + clip * frames * bins + b;
+    double s = 0.0;
+    long long t = t0;
+    // the loads do not depend on the recurrence: eight in flight per thread, then eight dependent updates
+    for (; t + 8 <= t1; t += 8) {
+      float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * sg_.bins);
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s = sg_.tau * s + k1 * (double)v[u];
+      for (int u = 0; u < 8; ++u) s = tau * s + k1 * (double)v[u];
+    }
+    for (; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
+    carry[(clip * bins + b) * n_chunks + j] = (float)s;
+  }
+  grid.sync();
+  // ---- (B) carry[j] <- state at the START of chunk j (in place); state[clip][bin] holds the clip's initial state
+  {
+    const int lane = threadIdx.x & 31;
+    const double dec = pow(tau, (double)chunk);   // every chunk but the last is full, and the last one's decay is unused
+    double dpow[5];                               // dec^(2^k)
+    dpow[0] = dec;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) dpow[k] = dpow[k - 1] * dpow[k - 1];
+    const double dec_lane = pow(dec, (double)lane), dec32 = dpow[4] * dpow[4];
+    for (long long w = tid >> 5; w < n_clips * bins; w += nthreads >> 5) {
+      float* __restrict__ c = carry + w * n_chunks;
+      double s = (double)state[w];               // state at the start of the current 32-chunk segment
+      for (long long j0 = 0; j0 < n_chunks; j0 += 32) {
+        const long long j = j0 + lane;
+        double y = j + 1 < n_chunks ? (double)__ldcg(c + j) : 0.0;   // inclusive decayed prefix sum of the locals
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double up = __shfl_up_sync(0xffffffffu, y, 1 << k);
+          if (lane >= (1 << k)) y = fma(dpow[k], up, y);
+        }
+        const double prev = __shfl_up_sync(0xffffffffu, y, 1);  // sum of the locals before this chunk
+        if (j < n_chunks) c[j] = (float)(fma(dec_lane, s, lane ? prev : 0.0));
+        s = fma(dec32, s, __shfl_sync(0xffffffffu, y, 31));
       }
-      for (; t < t1; ++t) s = sg_.tau * s + k1 * (double)__ldg(m + t * sg_.bins);
-      agg[flat] = (float)s;
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned* d = done + bid;
-    *d = sg_.epoch;
-  }
-  if (!live) return;
-  // (2) state at the start of chunk j: Horner over the aggregates of chunks 0 .. j-1
-  double acc = (double)state[clip * sg_.bins + b];
-  for (long long i = 0; i < j; ++i) {
-    const long long fi = flat - (j - i) * per_chunk;
-    const volatile unsigned* d = done + fi / blockDim.x;
-    while (*d != sg_.epoch) {}
-    __threadfence();
-    acc = fma(sg_.dec, acc, (double)__ldcg(agg + fi));
-  }
-  // (3) emit
-  typename OutElem<OUT>::type* __restrict__ o = out + clip * sg_.frames * sg_.bins + b;
-  float s = (float)acc;
-  long long t = t0;
-  for (; t + 8 <= t1; t += 8) {
-    float v[8];
+  grid.sync();
+  // ---- (C)
+  for (long long idx = tid; idx < total; idx += nthreads) {
+    const int b = (int)(idx % bins);
+    const long long cj = idx / bins, clip = cj / n_chunks, j = cj - clip * n_chunks;
+    const long long t0 = j * chunk, t1 = min(frames, t0 + (long long)chunk);
+    const float* __restrict__ m = mags + clip * frames * bins + b;
+    typename OutElem<OUT>::type* __restrict__ o = out + clip * frames * bins + b;
+    float s = __ldcg(carry + (clip * bins + b) * n_chunks + j);
+    long long t = t0;
+    for (; t + 8 <= t1; t += 8) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * sg_.bins);
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      s = finite_or_zero((float)(sg_.tau * (double)s + k1 * (double)v[u]));
-      o[(t + u) * sg_.bins] = emit_mag<OUT>(s, ep);
+      for (int u = 0; u < 8; ++u) {
+        s = finite_or_zero((float)(tau * (double)s + k1 * (double)v[u]));
+        o[(t + u) * bins] = emit_mag<OUT>(s, ep);
+      }
     }
+    for (; t < t1; ++t) {
+      s = finite_or_zero((float)(tau * (double)s + k1 * (double)__ldg(m + t * bins)));
+      o[t * bins] = emit_mag<OUT>(s, ep);
+    }
+    if (j == n_chunks - 1) state[clip * bins + b] = s;
   }
-  for (; t < t1; ++t) {
-    s = finite_or_zero((float)(sg_.tau * (double)s + k1 * (double)__ldg(m + t * sg_.bins)));
-    o[t * sg_.bins] = emit_mag<OUT>(s, ep);
-  }
-  if (j == sg_.n_chunks - 1) state[clip * sg_.bins + b] = s;
 }
 
 // re-emit a stored state vector (getByte/FloatFrequencyData called twice in one render quantum)

@@ -336,11 +336,10 @@ struct sg_engine {
   std::map<PlanKey, Plan> plans;
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
-  DevBuf scratch_mag, scratch_state, scratch_carry, scan_flags, d_in, d_out;
+  DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
   DevBuf d_raw[2];                   // interleaved PCM bytes in flight (sg_stft_pcm)
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
-  unsigned scan_epoch = 0;           // smooth_scan_kernel: a launch's `done` words take this value
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   const char* last_kernel = "none";
   std::mutex mu;
@@ -454,26 +453,25 @@ int launch_smooth_t(sg_engine* e, const float* mags, void* out, float* state, lo
   using T = typename sg::OutElem<OUT>::type;
   const long long n = n_clips * bins;
   if (n <= 0 || frames <= 0) return SG_OK;
-  // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run (one kernel:
-  // aggregates, decoupled look-back, emit)
+  // few (clip, bin) pairs and many frames: cut time into chunks so the GPU has threads to run (one cooperative
+  // kernel: chunk sums, carry scan, emit)
   const long long want_threads = 2048LL * e->sm_count;
   if (n < want_threads && frames >= 256) {
     const int chunk = (int)std::max<long long>(32, std::min<long long>(1024, frames * n / want_threads));
     const long long n_chunks = (frames + chunk - 1) / chunk;
     const long long nt = n * n_chunks, blocks = (nt + 255) / 256;
     SG_TRY(e->scratch_carry.reserve((size_t)nt * sizeof(float)));
-    // the flag words live in a buffer of their own: it only ever holds epochs of earlier launches (or zeros)
-    const size_t words = (size_t)blocks + 1;
-    if (words * sizeof(unsigned) > e->scan_flags.cap) {
-      SG_TRY(e->scan_flags.reserve(std::max<size_t>(2 * words, 4096) * sizeof(unsigned)));
-      SG_CUDA(cudaMemsetAsync(e->scan_flags.p, 0, e->scan_flags.cap, st));
-    }
-    float* agg = (float*)e->scratch_carry.p;
-    unsigned* ticket = (unsigned*)e->scan_flags.p;
-    unsigned* done = ticket + 1;
-    SG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-    sg::ScanGeom sgm{n_clips, frames, n_chunks, bins, chunk, tau, std::pow(tau, (double)chunk), ++e->scan_epoch};
-    sg::smooth_scan_kernel<OUT><<<(unsigned)blocks, 256, 0, st>>>(mags, (T*)out, state, agg, done, ticket, sgm, ep);
+    float* carry = (float*)e->scratch_carry.p;
+    // cooperative launch: the whole grid must be resident for its two grid barriers
+    static int per_sm[sg::kMaxDevices] = {};
+    int& occ = per_sm[e->device >= 0 && e->device < sg::kMaxDevices ? e->device : 0];
+    if (occ == 0) SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sg::smooth_scan_kernel<OUT>, 256, 0));
+    const unsigned grid = (unsigned)std::min<long long>(blocks, (long long)occ * e->sm_count);
+    sg::ScanGeom sgm{n_clips, frames, n_chunks, bins, chunk, tau};
+    T* out_t = (T*)out;
+    sg::Epilogue ep_c = ep;
+    void* args[] = {(void*)&mags, (void*)&out_t, (void*)&state, (void*)&carry, (void*)&sgm, (void*)&ep_c};
+    SG_CUDA(cudaLaunchCooperativeKernel((const void*)sg::smooth_scan_kernel<OUT>, dim3(grid), dim3(256), args, 0, st));
     e->launches++;
     SG_CUDA(cudaGetLastError());
     return SG_OK;
@@ -521,7 +519,7 @@ int run_range(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const flo
   // enough for the magnitudes to stay in L2 between the two kernels (they are written and read once and the tile
   // buffer is reused, so they never reach HBM: DRAM traffic stays at the algorithmic bytes).  A tile is a group of
   // whole clips, or a frame range of one clip chained through `state`.
-  const size_t kTileBytes = 40u << 20;
+  const size_t kTileBytes = 56u << 20;
   const size_t frame_bytes = (size_t)bins * sizeof(float);
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * cfg.n_fft, lut);
   const long long tile_frames = std::max<long long>(1, (long long)(kTileBytes / frame_bytes));
@@ -627,7 +625,7 @@ int sg_engine_destroy(sg_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
-  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->scan_flags.release(); e->d_in.release(); e->d_out.release();
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->d_in.release(); e->d_out.release();
   e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
