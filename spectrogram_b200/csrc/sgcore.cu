@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -515,11 +516,13 @@ int run_range(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const flo
     }
     return SG_OK;
   }
-  // tau > 0 on a shape without a fused kernel: frame kernel -> linear magnitudes -> recurrence kernel, in tiles small
-  // enough for the magnitudes to stay in L2 between the two kernels (they are written and read once and the tile
-  // buffer is reused, so they never reach HBM: DRAM traffic stays at the algorithmic bytes).  A tile is a group of
-  // whole clips, or a frame range of one clip chained through `state`.
-  const size_t kTileBytes = 56u << 20;
+  // tau > 0 on a shape without a fused kernel: frame kernel -> linear magnitudes (scratch) -> recurrence kernel, in
+  // tiles of whole clips, or frame ranges of one clip chained through `state`.  Tiles small enough to keep the
+  // magnitudes in L2 between the two kernels were measured and lose: 64 x 60 s clips at n_fft 2048 take 2.54 ms with
+  // 56 MB tiles (64 launches), 2.09 ms with 160 MB, 1.63 ms with one 1.4 GB tile (tools/tau_tile_sweep.py) -- a tile
+  // has to fill the GPU several times over before the launch gaps and the pipeline fill stop showing.  So the tile is
+  // bounded by memory only (SG_TAU_TILE_MB overrides it for the sweep).
+  static const size_t kTileBytes = [] { const char* v = getenv("SG_TAU_TILE_MB"); return (size_t)(v ? atoi(v) : 1024) << 20; }();
   const size_t frame_bytes = (size_t)bins * sizeof(float);
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * cfg.n_fft, lut);
   const long long tile_frames = std::max<long long>(1, (long long)(kTileBytes / frame_bytes));
