@@ -53,6 +53,10 @@ struct SmemPlan {       // generic mixed-radix kernel
 // Launchers: enqueue on `st`, return the cudaError_t of the launch (0 = ok).  `out_kind` is kOut*.
 int launch_w32x2p(int out_kind, int warps, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out,
                   int sm_count, int device, cudaStream_t st);
+struct XsGeom;   // kernel_w32x2s.cuh
+// grid = CTAs to launch (<= sm_count: the chained tasks and the look-back need every CTA resident)
+int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Plan& p, const Epilogue& ep, void* out,
+                  int grid, int device, cudaStream_t st);
 int launch_w32x2(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);
 int launch_w32(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilogue& ep, void* out, int sm_count,

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernel_misc.cuh"
+#include "kernel_w32x2s.cuh"
 #include "kernel_pcm.cuh"
 #include "plans.cuh"
 using sg::PcmMix; using sg::PcmGeom; using sg::kPcmMaxChannels; using sg::pcm_tile_frames; using sg::launch_pcm_ingest;
@@ -338,6 +339,8 @@ struct sg_engine {
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
   DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
+  DevBuf xs_carry, xs_flags;         // fused-smoothing kernel: per-segment carry vectors and their ready flags
+  unsigned xs_epoch = 0;
   DevBuf d_raw[2];                   // interleaved PCM bytes in flight (sg_stft_pcm)
   PinBuf pin_in[2], pin_out[2];
   int64_t launches = 0;
@@ -494,6 +497,69 @@ int launch_smooth(sg_engine* e, int out_kind, const float* mags, void* out, floa
   }
 }
 
+// tau > 0 at n_fft 2048 / hop 512 or 256: the recurrence fused into the frame-pair kernel (kernel_w32x2s.cuh), one launch,
+// no magnitude scratch.  Returns SG_OK with *done = false when the shape is not served.
+int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const float* pcm_dev, long long n_clips,
+                           long long clip_len, long long clip_stride, long long start0, long long nframes,
+                           long long out_clip_rows, void* out, float* state, const uint32_t* lut, cudaStream_t st,
+                           bool* done) {
+  *done = false;
+  const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
+  if (pl.n_fft != sg::kW32N || (cfg.hop != 512 && cfg.hop != 256) || e->kernel_variant != 0) return SG_OK;
+  if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
+  const int grid_max = e->sm_count, nw = 12;
+  sg::XsGeom x;
+  x.n_clips = n_clips;
+  x.out_clip_rows = out_clip_rows;
+  auto even_up = [](long long v) { return (v + 1) & ~1LL; };
+  long long segs, seg_frames;
+  if (2 * n_clips <= grid_max) {
+    // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
+    seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
+    x.mode = 1;
+  } else {
+    // chained segments: pick the split that fills whole waves of CTAs best, segments of at least four rounds of pairs
+    long long best_s = 1;
+    double best_eff = 0.0;
+    for (long long s_try = 1; s_try <= 64; ++s_try) {
+      const long long sf = even_up((nframes + s_try - 1) / s_try);
+      if (s_try > 1 && sf < 8 * nw) break;
+      const long long tasks = ((nframes + sf - 1) / sf) * n_clips, waves = (tasks + grid_max - 1) / grid_max;
+      const double eff = (double)tasks / (double)(waves * grid_max);
+      if (eff > best_eff + 0.005) { best_eff = eff; best_s = s_try; }
+    }
+    seg_frames = even_up((nframes + best_s - 1) / best_s);
+    x.mode = 0;
+  }
+  segs = (nframes + seg_frames - 1) / seg_frames;
+  const long long tasks = segs * n_clips;
+  if (tasks >= (1LL << 31)) return SG_OK;
+  x.seg_frames = (int)seg_frames;
+  x.segs = (int)segs;
+  x.tau = cfg.smoothing;
+  x.mscale = (float)((1.0 - (double)cfg.smoothing) / (2.0 * pl.n_fft));
+  x.dec = (float)std::pow((double)cfg.smoothing, (double)seg_frames);
+  x.state_in = state;
+  x.state_out = state;
+  SG_TRY(e->xs_carry.reserve((size_t)tasks * 512 * sizeof(float2)));
+  if ((size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
+    SG_TRY(e->xs_flags.reserve(std::max<size_t>(2 * (size_t)tasks, 4096) * sizeof(unsigned)));
+    SG_CUDA(cudaMemsetAsync(e->xs_flags.p, 0, e->xs_flags.cap, st));   // flags only ever hold epochs of earlier launches
+  }
+  x.carry = (float2*)e->xs_carry.p;
+  x.flags = (unsigned*)e->xs_flags.p;
+  x.epoch = ++e->xs_epoch;
+  sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
+  const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+  const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
+  const int grid = (int)std::min<long long>(tasks, grid_max);
+  SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
+  e->launches++;
+  e->last_kernel = "warp32x32x2s";
+  *done = true;
+  return SG_OK;
+}
+
 // One launch group over `n_clips` clips x frames [t0, t0+nframes) of each clip.
 // tau == 0: a single fused kernel.  tau > 0: frame kernel -> linear magnitudes (scratch) ->
 // recurrence + dB/byte kernel, chained through `state` ([n_clips][bins]).
@@ -515,6 +581,13 @@ int run_range(sg_engine* e, const Plan& pl, const sg_stft_config& cfg, const flo
       SG_TRY(launch_frames(e, pl, g, cfg, cfg.output, lut, o, st));
     }
     return SG_OK;
+  }
+  {
+    bool fused = false;
+    char* o = (char*)out_dev + (size_t)t0 * bins * eb;
+    SG_TRY(launch_fused_smoothing(e, pl, cfg, pcm_dev, n_clips, clip_len, clip_stride, start0, nframes, frames_total, o, state,
+                                  lut, st, &fused));
+    if (fused) return SG_OK;
   }
   // tau > 0 on a shape without a fused kernel: frame kernel -> linear magnitudes (scratch) -> recurrence kernel, in
   // tiles of whole clips, or frame ranges of one clip chained through `state`.  Tiles small enough to keep the
@@ -628,7 +701,7 @@ int sg_engine_destroy(sg_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
-  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->d_in.release(); e->d_out.release();
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->xs_carry.release(); e->xs_flags.release(); e->d_in.release(); e->d_out.release();
   e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);

@@ -544,3 +544,64 @@ def test_time_parallel_scan_agrees_with_the_sequential_recurrence(engine):
         else:
             d = np.abs(a.astype(np.int32) - b.astype(np.int32))
             assert d.max() <= 1 and (d != 0).mean() < 1e-4
+
+
+# ----------------------------------------------------------------------------- fused smoothing kernel (n_fft 2048, tau > 0)
+@pytest.mark.parametrize("n_clips,clip_len,hop,align", [
+    (1, 2048 + 511 * 512, 512, O.ALIGN_VALID),        # few clips: aggregate pass + look-back + emit pass, even frames
+    (3, 2048 + 300 * 512 + 77, 512, O.ALIGN_ANALYSER),  # zero history at the start, odd frame count
+    (2, 2048 + 700 * 256, 256, O.ALIGN_VALID),        # hop 256 instantiation
+    (160, 2048 + 120 * 512, 512, O.ALIGN_VALID),      # more clips than half the SMs: chained segments
+    (301, 2048 + 97 * 512, 512, O.ALIGN_ANALYSER),    # chained, odd frames per clip, several tasks per CTA
+])
+def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, hop, align):
+    rng = np.random.default_rng(n_clips)
+    x = (0.05 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    x += O.chirp(clip_len, 44100.0, 100.0, 15000.0, 0.3)[None, :]
+    sel = np.unique(np.r_[0, 1, n_clips // 2, n_clips - 1])
+    cfg = O.Config(n_fft=2048, hop=hop, smoothing=0.8, align=align, output=O.OUT_F32_MAG)
+    ref_mag = O.spectrogram(x[sel], cfg)
+    for out in ("mag", "db", "u8", "rgba"):
+        opts = sg.Options(fftSize=2048, hop=hop, output=out, smoothingTimeConstant=0.8, align=ALIGN[align])
+        got = engine.spectrogram(x, opts)
+        assert engine.last_kernel == "warp32x32x2s"
+        if out == "mag":
+            assert_mag_close(got[sel], ref_mag)
+        elif out == "db":
+            assert_db_close(got[sel], ref_mag)
+        elif out == "u8":
+            got_u8 = got
+            assert_bytes_close(got[sel], O.finish(ref_mag, O.Config(n_fft=2048, hop=hop, smoothing=0.8, align=align)))
+        else:
+            assert np.array_equal(got, O.colormap_lut()[got_u8])
+
+
+def test_fused_smoothing_chained_segments_are_the_sequential_arithmetic(engine):
+    """Chain mode hands the float state from segment to segment: cutting a clip into segments must not change a bit.
+    The same clips as a small batch (few mode, look-back over float aggregates) agree to rounding."""
+    rng = np.random.default_rng(5)
+    clip_len = 2048 + 400 * 512
+    x = (0.2 * rng.standard_normal((200, clip_len))).astype(np.float32)
+    opts = sg.Options(fftSize=2048, hop=512, output="mag", smoothingTimeConstant=0.75)
+    a = engine.spectrogram(x, opts)                    # 200 clips: chained segments
+    b = engine.spectrogram(x[:150], opts)              # another split of the same clips
+    assert np.array_equal(a[:150], b)
+    c = engine.spectrogram(x[:2], opts)                # few mode
+    assert np.max(np.abs(c - a[:2]) / (np.abs(a[:2]) + 1e-30)) < 5e-6
+
+
+def test_fused_smoothing_non_finite_frames_reset_the_state(engine):
+    rng = np.random.default_rng(8)
+    clip_len = 2048 + 60 * 512
+    x = (0.2 * rng.standard_normal((2, clip_len))).astype(np.float32)
+    x[0, 2048 + 20 * 512 + 5] = np.nan        # four frames of clip 0 see the NaN
+    x[1, 2048 + 30 * 512 + 9] = np.inf
+    cfg = O.Config(n_fft=2048, hop=512, smoothing=0.8, output=O.OUT_F32_MAG)
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = O.spectrogram(x, cfg)
+    got = engine.spectrogram(x, sg.Options(fftSize=2048, hop=512, output="mag", smoothingTimeConstant=0.8))
+    assert engine.last_kernel == "warp32x32x2s"
+    for c in (0, 1):
+        bad = np.all(ref[c] == 0, axis=1)
+        assert bad.sum() == 4 and np.all(got[c][bad] == 0)
+    assert_mag_close(got, ref)
