@@ -84,7 +84,8 @@ __device__ __forceinline__ int xs_bin(int i, int lane, int half) {
   return half == 0 ? k : ((i == 0 && lane == 0) ? 512 : kW32M - k);
 }
 
-template <int OUT, int NW, int HOPJ>
+// LATE: the next pair's loads are issued after the turn has been passed on (in the epilogue) instead of inside the untangle
+template <int OUT, int NW, int HOPJ, bool LATE>
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
@@ -274,10 +275,12 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       // (1 - tau) |X| / N of both frames
       pk[i] = mul2(P2(sqrt_ftz(qk.v.x), sqrt_ftz(qk.v.y)), bc(x.mscale));
       pm[i] = mul2(P2(sqrt_ftz(qm.v.x), sqrt_ftz(qm.v.y)), bc(x.mscale));
-      static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
-        constexpr int m = decltype(mm)::value;
-        s[m] = ldg_nc_f2(nsrc + 32 * m);
-      });
+      if constexpr (!LATE) {
+        static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
+          constexpr int m = decltype(mm)::value;
+          s[m] = ldg_nc_f2(nsrc + 32 * m);
+        });
+      }
     });
     const bool dirty = __any_sync(0xffffffffu, worst >= 0x7f800000u);
 
@@ -368,6 +371,9 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     }
     __syncwarp();
     if (lane0) mbar_arrive(s_bar + (warp + 1 == NW ? 0 : warp + 1));
+    if constexpr (LATE) {
+      static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + 32 * m); });
+    }
 
     // ---- epilogue: X^ -> dB / byte / colour of both frames (nothing to write in the aggregate pass)
     if (cur.kind != 1) {

@@ -558,7 +558,7 @@ def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, ho
     rng = np.random.default_rng(n_clips)
     x = (0.05 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
     x += O.chirp(clip_len, 44100.0, 100.0, 15000.0, 0.3)[None, :]
-    sel = np.unique(np.r_[0, 1, n_clips // 2, n_clips - 1])
+    sel = np.unique(np.r_[0, min(1, n_clips - 1), n_clips // 2, n_clips - 1])
     cfg = O.Config(n_fft=2048, hop=hop, smoothing=0.8, align=align, output=O.OUT_F32_MAG)
     ref_mag = O.spectrogram(x[sel], cfg)
     for out in ("mag", "db", "u8", "rgba"):
