@@ -41,7 +41,7 @@ struct XsGeom {
 constexpr int kXsStateBytes = 16 * 32 * 8;
 template <int NW>
 struct XsShape {
-  static constexpr int kSmemBytes = XpShape<NW>::kSmemBytes + kXsStateBytes + NW * 8;
+  static constexpr int kSmemBytes = XpShape<NW>::kSmemBytes + kXsStateBytes + 4 * NW * 8;   // up to 4 turn chains
 };
 
 // the work item a pair belongs to: (segment, clip) and what to do at its first / last pair
@@ -85,7 +85,7 @@ __device__ __forceinline__ int xs_bin(int i, int lane, int half) {
 }
 
 // LATE: the next pair's loads are issued after the turn has been passed on (in the epilogue) instead of inside the untangle
-template <int OUT, int NW, int HOPJ, bool LATE>
+template <int OUT, int NW, int HOPJ, bool LATE, int K>
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
@@ -95,9 +95,9 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
   float2* s_ut = s_twb + 5 * 32;                                       // [16][32] W_2048^{lane + 32 i}
   float2* s_state = s_ut + 16 * 32;                                    // [16][32] (X^[k], X^[mirror k])
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_state + 16 * 32);    // [NW] the turn of warp w
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_state + 16 * 32);    // [K][NW] the turn of warp w on slot group c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* wbase = reinterpret_cast<unsigned char*>(s_bar + NW) + warp * kXpWarpBytes;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(s_bar + 4 * NW) + warp * kXpWarpBytes;
   float4* xp = reinterpret_cast<float4*>(wbase);                       // exchange planes
   uint16_t* sb16 = reinterpret_cast<uint16_t*>(wbase);                 // byte stage: aliases the planes
 
@@ -113,10 +113,10 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       s_twb[i] = __ldg(pl.tw2 + ((1 << u) - 1) * 32 + l);
     }
     for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) s_ut[i] = __ldg(pl.ut + i);
-    if (threadIdx.x < NW) mbar_init(s_bar + threadIdx.x, 1);
+    if (threadIdx.x < K * NW) mbar_init(s_bar + threadIdx.x, 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) mbar_arrive(s_bar);      // warp 0 holds the first turn
+  if (threadIdx.x < K) mbar_arrive(s_bar + threadIdx.x * NW);      // warp 0 holds the first turn of every group
   unsigned turn = 0;                             // phase parity of this warp's next wait
 
   const int fpc = (int)g.frames_per_clip;
@@ -284,69 +284,91 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     });
     const bool dirty = __any_sync(0xffffffffu, worst >= 0x7f800000u);
 
-    // ---- the recurrence, in pair order: wait for this warp's turn, update the segment's state, pass the turn on
-    while (!mbar_try_wait(s_bar + warp, turn)) {}
-    turn ^= 1;
-    if (p == 0) {
-      // first pair of a work item: the state the segment starts from
-      if (cur.kind == 1 || (cur.seg == 0 && x.state_in == nullptr)) {
-        static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = make_float2(0.f, 0.f); });
-      } else if (cur.seg == 0) {
-        const float* __restrict__ si = x.state_in + (long long)cur.clip * kW32M;
-        static_for<0, 16>([&](auto ii) {
-          constexpr int i = decltype(ii)::value;
-          s_state[i * 32 + lane] = make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]);
-        });
-      } else if (cur.kind == 0) {
-        const long long prev = (long long)(cur.seg - 1) * x.n_clips + cur.clip;
-        if (lane0) while (ld_acquire_u32(x.flags + prev) != x.epoch) {}
-        __syncwarp();
-        const float2* __restrict__ c = x.carry + prev * 512 + lane;
-        static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = __ldcg(c + i * 32); });
-      } else {
-        // look-back: state at the start of segment s = dec^s state_in + sum_{j < s} dec^(s-1-j) aggregate_j
-        // (Horner, accumulated in the shared state itself: no registers to spare here)
-        const float* __restrict__ si = x.state_in ? x.state_in + (long long)cur.clip * kW32M : nullptr;
-        static_for<0, 16>([&](auto ii) {
-          constexpr int i = decltype(ii)::value;
-          s_state[i * 32 + lane] =
-              si ? make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
-        });
-        for (int j = 0; j < cur.seg; ++j) {
-          const long long tj = (long long)j * x.n_clips + cur.clip;
-          if (lane0) while (ld_acquire_u32(x.flags + tj) != x.epoch) {}
-          __syncwarp();
-          const float2* __restrict__ c = x.carry + tj * 512 + lane;
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const float2 v = __ldcg(c + i * 32), o = s_state[i * 32 + lane];
-            s_state[i * 32 + lane] = make_float2(fmaf(x.dec, o.x, v.x), fmaf(x.dec, o.y, v.y));
-          }
-        }
+    // ---- the recurrence, in pair order.  The 16 state slots of a lane are cut into K groups with a turn of their
+    //      own each, so warp w + 1 updates group c while warp w is already on group c + 1: the ordered part of the
+    //      kernel is pipelined K deep.  In the aggregate pass (kind 1) the sign bit of a state value records that a
+    //      non-finite frame wiped that bin inside this segment (X^ itself is never negative): the look-back must
+    //      then drop what came in from earlier segments.
+    if (p == 0 && cur.kind != 1 && cur.seg > 0) {
+      // the segments this one starts from must have been published (chain: the previous one; look-back: all of them)
+      if (lane0) {
+        for (int j = cur.kind == 0 ? cur.seg - 1 : 0; j < cur.seg; ++j)
+          while (ld_acquire_u32(x.flags + (long long)j * x.n_clips + cur.clip) != x.epoch) {}
       }
       __syncwarp();
     }
-    if (!dirty) {
-      static_for<0, 16>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const float2 st = s_state[i * 32 + lane];
-        const float ka = fmaf(x.tau, st.x, pk[i].v.x), kb = fmaf(x.tau, ka, pk[i].v.y);
-        const float ma = fmaf(x.tau, st.y, pm[i].v.x), mb = fmaf(x.tau, ma, pm[i].v.y);
-        pk[i] = P2(ka, kb);
-        pm[i] = P2(ma, mb);
-        s_state[i * 32 + lane] = has_b ? make_float2(kb, mb) : make_float2(ka, ma);
-      });
-    } else {
-      static_for<0, 16>([&](auto ii) {   // [SPEC] a non-finite X^ is set to 0
-        constexpr int i = decltype(ii)::value;
-        const float2 st = s_state[i * 32 + lane];
-        const float ka = finite_or_zero(fmaf(x.tau, st.x, pk[i].v.x)), kb = finite_or_zero(fmaf(x.tau, ka, pk[i].v.y));
-        const float ma = finite_or_zero(fmaf(x.tau, st.y, pm[i].v.x)), mb = finite_or_zero(fmaf(x.tau, ma, pm[i].v.y));
-        pk[i] = P2(ka, kb);
-        pm[i] = P2(ma, mb);
-        s_state[i * 32 + lane] = has_b ? make_float2(kb, mb) : make_float2(ka, ma);
-      });
-    }
+    static_for<0, K>([&](auto cc) {
+      constexpr int c = decltype(cc)::value, i0 = c * (16 / K), i1 = i0 + 16 / K;
+      while (!mbar_try_wait(s_bar + c * NW + warp, turn)) {}
+      if (p == 0) {
+        // first pair of a work item: the state the segment starts from
+        const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
+        if (cur.kind == 1 || cur.seg == 0) {
+          static_for<i0, i1>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            s_state[i * 32 + lane] =
+                si ? make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
+          });
+        } else if (cur.kind == 0) {
+          const float2* __restrict__ cv = x.carry + ((long long)(cur.seg - 1) * x.n_clips + cur.clip) * 512 + lane;
+          static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = __ldcg(cv + i * 32); });
+        } else {
+          // look-back: state at the start of segment s = dec^s state_in + sum_{j < s} dec^(s-1-j) aggregate_j (Horner);
+          // an aggregate with its sign bit set wipes what came before it
+          float2 acc[16 / K];
+          static_for<i0, i1>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            acc[i - i0] = si ? make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
+          });
+          for (int j = 0; j < cur.seg; ++j) {
+            const float2* __restrict__ cv = x.carry + ((long long)j * x.n_clips + cur.clip) * 512 + lane;
+            static_for<i0, i1>([&](auto ii) {
+              constexpr int i = decltype(ii)::value;
+              const float2 v = __ldcg(cv + i * 32);
+              acc[i - i0] = make_float2(fmaf(signbit(v.x) ? 0.f : x.dec, acc[i - i0].x, fabsf(v.x)),
+                                        fmaf(signbit(v.y) ? 0.f : x.dec, acc[i - i0].y, fabsf(v.y)));
+            });
+          }
+          static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = acc[i - i0]; });
+        }
+        __syncwarp();
+      }
+      if (!dirty && cur.kind != 1) {
+        static_for<i0, i1>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          const float2 st = s_state[i * 32 + lane];
+          const float ka = fmaf(x.tau, st.x, pk[i].v.x), kb = fmaf(x.tau, ka, pk[i].v.y);
+          const float ma = fmaf(x.tau, st.y, pm[i].v.x), mb = fmaf(x.tau, ma, pm[i].v.y);
+          pk[i] = P2(ka, kb);
+          pm[i] = P2(ma, mb);
+          s_state[i * 32 + lane] = has_b ? make_float2(kb, mb) : make_float2(ka, ma);
+        });
+      } else {
+        static_for<i0, i1>([&](auto ii) {   // [SPEC] a non-finite X^ is set to 0 (and, kind 1, remembered in the sign)
+          constexpr int i = decltype(ii)::value;
+          const float2 st = s_state[i * 32 + lane];
+          const float ka0 = fmaf(x.tau, fabsf(st.x), pk[i].v.x), ka = finite_or_zero(ka0);
+          const float kb0 = fmaf(x.tau, ka, pk[i].v.y), kb = finite_or_zero(kb0);
+          const float ma0 = fmaf(x.tau, fabsf(st.y), pm[i].v.x), ma = finite_or_zero(ma0);
+          const float mb0 = fmaf(x.tau, ma, pm[i].v.y), mb = finite_or_zero(mb0);
+          pk[i] = P2(ka, kb);
+          pm[i] = P2(ma, mb);
+          float nk = has_b ? kb : ka, nm = has_b ? mb : ma;
+          if (cur.kind == 1) {
+            const bool wk = signbit(st.x) || !(fabsf(ka0) <= 3.4028235e38f) || (has_b && !(fabsf(kb0) <= 3.4028235e38f));
+            const bool wm = signbit(st.y) || !(fabsf(ma0) <= 3.4028235e38f) || (has_b && !(fabsf(mb0) <= 3.4028235e38f));
+            nk = wk ? -nk : nk;
+            nm = wm ? -nm : nm;
+            pk[i] = P2(nk, nk);     // no output in this pass: the registers only feed the carry-out below
+            pm[i] = P2(nm, nm);
+          }
+          s_state[i * 32 + lane] = make_float2(nk, nm);
+        });
+      }
+      __syncwarp();
+      if (lane0) mbar_arrive(s_bar + c * NW + (warp + 1 == NW ? 0 : warp + 1));
+    });
+    turn ^= 1;
     const bool last = p == (cur.nfr + 1) / 2 - 1;
     if (last && !(cur.kind == 2 && cur.seg + 1 < x.segs)) {
       // last pair of a work item: hand the state to the next segment (or to the caller)
@@ -369,8 +391,6 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
         });
       }
     }
-    __syncwarp();
-    if (lane0) mbar_arrive(s_bar + (warp + 1 == NW ? 0 : warp + 1));
     if constexpr (LATE) {
       static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + 32 * m); });
     }
