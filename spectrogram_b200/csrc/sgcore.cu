@@ -339,7 +339,7 @@ struct sg_engine {
   uint32_t* lut_ref = nullptr;       // device, reference colour map
   DevBuf lut_user;                   // device copy of cfg.colormap
   DevBuf scratch_mag, scratch_state, scratch_carry, d_in, d_out;
-  DevBuf xs_carry, xs_flags;         // fused-smoothing kernel: per-segment carry vectors and their ready flags
+  DevBuf xs_carry, xs_flags, xs_state;         // fused-smoothing kernel: per-segment carry vectors and their ready flags
   unsigned xs_epoch = 0;
   DevBuf d_raw[2];                   // interleaved PCM bytes in flight (sg_stft_pcm)
   PinBuf pin_in[2], pin_out[2];
@@ -507,7 +507,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
   if (pl.n_fft != sg::kW32N || (cfg.hop != 512 && cfg.hop != 256) || e->kernel_variant != 0) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
-  const int grid_max = e->sm_count, nw = 12;
+  const int grid_max = e->sm_count, nw = sg::kXsProducers;
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
@@ -541,9 +541,16 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   x.dec = (float)std::pow((double)cfg.smoothing, (double)seg_frames);
   x.state_in = state;
   x.state_out = state;
+  const size_t state_bytes = (size_t)n_clips * sg::kW32M * sizeof(float);
+  if (x.mode == 1) {
+    // the segments of a clip run concurrently and every one of them reads the clip's initial state: the final state
+    // goes to a buffer of its own and is copied over afterwards
+    SG_TRY(e->xs_state.reserve(state_bytes));
+    x.state_out = (float*)e->xs_state.p;
+  }
   SG_TRY(e->xs_carry.reserve((size_t)tasks * 512 * sizeof(float2)));
-  if ((size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
-    SG_TRY(e->xs_flags.reserve(std::max<size_t>(2 * (size_t)tasks, 4096) * sizeof(unsigned)));
+  if (2 * (size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
+    SG_TRY(e->xs_flags.reserve(std::max<size_t>(4 * (size_t)tasks, 4096) * sizeof(unsigned)));
     SG_CUDA(cudaMemsetAsync(e->xs_flags.p, 0, e->xs_flags.cap, st));   // flags only ever hold epochs of earlier launches
   }
   x.carry = (float2*)e->xs_carry.p;
@@ -554,6 +561,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
   const int grid = (int)std::min<long long>(tasks, grid_max);
   SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
+  if (x.mode == 1) SG_CUDA(cudaMemcpyAsync(state, x.state_out, state_bytes, cudaMemcpyDeviceToDevice, st));
   e->launches++;
   e->last_kernel = "warp32x32x2s";
   *done = true;
@@ -701,7 +709,7 @@ int sg_engine_destroy(sg_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->plans) kv.second.release();
   cudaFree(e->lut_ref);
-  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->xs_carry.release(); e->xs_flags.release(); e->d_in.release(); e->d_out.release();
+  e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->xs_carry.release(); e->xs_flags.release(); e->xs_state.release(); e->d_in.release(); e->d_out.release();
   e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
   cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
