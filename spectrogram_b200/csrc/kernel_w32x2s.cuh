@@ -47,7 +47,7 @@ struct XsGeom {
 };
 
 constexpr int kXsProducers = 10, kXsConsumers = 2, kXsWarps = kXsProducers + kXsConsumers;
-constexpr int kXsStageBytes = 2 * 2048;                                // two byte stages of 1024 (A, B) pairs
+constexpr int kXsStageBytes = 2 * 1024;                                // per consumer: 512 (A, B) byte pairs
 constexpr int kXsSmemBytes = kXpTableBytes + kXsStageBytes + 2 * kXsProducers * 8 + kXsProducers * kXpWarpBytes;
 constexpr int kXsMaxRegs = (65536 / (kXsWarps * 32)) / 8 * 8;
 
@@ -100,8 +100,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
   float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
   float2* s_ut = s_twb + 5 * 32;                                       // [16][32] W_2048^{lane + 32 i}
-  uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_ut + 16 * 32);     // [2][1024] (A, B) byte pairs of a frame pair
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + 2 * 1024);  // [NP] producer w's powers are in its planes
+  uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_ut + 16 * 32);     // [2][512] (A, B) byte pairs, one stage per consumer
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + 2 * 512);  // [NP] producer w's powers are in its planes
   uint64_t* s_empty = s_full + NP;                                     // [NP] both consumers have read them
   unsigned char* planes = reinterpret_cast<unsigned char*>(s_empty + NP);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,19 +129,21 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
 
   if (warp >= NP) {
     // =================================================================================== consumer
-    const int c = warp - NP, i0 = 8 * c;
-    float2 st[8];                           // X^ of this consumer's slots: (bin lane + 32 i, its mirror)
+    // consumer 0 owns the bins a lane computes directly (k = lane + 32 i < 512), consumer 1 their mirrors (bins 513 ..
+    // 1023, and bin 512 in lane 0's slot 0): each keeps X^ of its 512 bins in registers and writes its half of the rows
+    const int c = warp - NP;
+    uint16_t* sb16 = s_stage + c * 512;     // this consumer's byte stage: 512 (A, B) pairs
+    float st[16];                           // X^ of this consumer's bins: slot i of every lane
     unsigned full_par = 0;
     int w = 0;                              // producer that delivers the current pair
-    unsigned q = 0;                         // pairs consumed (stage parity)
     for (XsItem cur = xs_item(x, fpc, 0); cur.valid; cur = xs_item(x, fpc, cur.it + 1)) {
       const int npairs = (cur.nfr + 1) / 2;
       // ---- first pair of a work item: the state the segment starts from
       {
         const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
-        static_for<0, 8>([&](auto ii) {
+        static_for<0, 16>([&](auto ii) {
           constexpr int i = decltype(ii)::value;
-          st[i] = si ? make_float2(si[xs_bin(i0 + i, lane, 0)], si[xs_bin(i0 + i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
+          st[i] = si ? si[xs_bin(i, lane, c) & (kW32M - 1)] : 0.f;
         });
         if (cur.kind != 1 && cur.seg > 0) {
           // chain: the previous segment's final state; look-back: Horner over the aggregates of all earlier segments,
@@ -150,13 +152,12 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
             const long long tj = (long long)j * x.n_clips + cur.clip;
             if (lane0) while (ld_acquire_u32(x.flags + 2 * tj + c) != x.epoch) {}
             __syncwarp();
-            const float2* __restrict__ cv = x.carry + tj * 512 + i0 * 32 + lane;
-            static_for<0, 8>([&](auto ii) {
+            const float* __restrict__ cv = reinterpret_cast<const float*>(x.carry) + (tj * 2 + c) * 512 + lane;
+            static_for<0, 16>([&](auto ii) {
               constexpr int i = decltype(ii)::value;
-              const float2 v = __ldcg(cv + i * 32);
+              const float v = __ldcg(cv + i * 32);
               if (cur.kind == 0) st[i] = v;
-              else st[i] = make_float2(fmaf(signbit(v.x) ? 0.f : x.dec, st[i].x, fabsf(v.x)),
-                                       fmaf(signbit(v.y) ? 0.f : x.dec, st[i].y, fabsf(v.y)));
+              else st[i] = fmaf(signbit(v) ? 0.f : x.dec, st[i], fabsf(v));
             });
           }
         }
@@ -165,104 +166,98 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
         const bool has_b = 2 * p + 1 < cur.nfr;
         // ---- the pair's powers from producer w's planes
         while (!mbar_try_wait(s_full + w, full_par)) {}
-        const float4* __restrict__ src = reinterpret_cast<const float4*>(planes + w * kXpWarpBytes) + i0 * 32 + lane;
-        float4 pw[8];
-        static_for<0, 8>([&](auto ii) { constexpr int i = decltype(ii)::value; pw[i] = src[i * 32]; });
+        const float2* __restrict__ src = reinterpret_cast<const float2*>(planes + w * kXpWarpBytes) + c * 512 + lane;
+        float2 pw[16];
+        static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; pw[i] = src[i * 32]; });
         __syncwarp();
         if (lane0) mbar_arrive(s_empty + w);
         if (++w == NP) { w = 0; full_par ^= 1; }
-        // ---- the recurrence for frames A then B; [SPEC] a non-finite X^ is set to 0
-        P2 vk[8], vm[8];                      // X^ of (frame A, frame B) at the bin and at its mirror
-        static_for<0, 8>([&](auto ii) {
+        // ---- the recurrence for frames A then B.  [SPEC] a non-finite X^ is set to 0: one integer max over the
+        //      lane's powers decides whether the per-value path is needed (Inf and NaN have the largest bit patterns)
+        unsigned worst = 0;
+        static_for<0, 16>([&](auto ii) {
           constexpr int i = decltype(ii)::value;
-          const float ka0 = fmaf(x.tau, fabsf(st[i].x), sqrt_ftz(pw[i].x) * x.mscale), ka = finite_or_zero(ka0);
-          const float kb0 = fmaf(x.tau, ka, sqrt_ftz(pw[i].y) * x.mscale), kb = finite_or_zero(kb0);
-          const float ma0 = fmaf(x.tau, fabsf(st[i].y), sqrt_ftz(pw[i].z) * x.mscale), ma = finite_or_zero(ma0);
-          const float mb0 = fmaf(x.tau, ma, sqrt_ftz(pw[i].w) * x.mscale), mb = finite_or_zero(mb0);
-          vk[i] = P2(ka, kb);
-          vm[i] = P2(ma, mb);
-          float nk = has_b ? kb : ka, nm = has_b ? mb : ma;
-          if (cur.kind == 1) {   // aggregate pass: remember in the sign that the bin was wiped inside this segment
-            const bool wk = signbit(st[i].x) || !(fabsf(ka0) <= 3.4028235e38f) || (has_b && !(fabsf(kb0) <= 3.4028235e38f));
-            const bool wm = signbit(st[i].y) || !(fabsf(ma0) <= 3.4028235e38f) || (has_b && !(fabsf(mb0) <= 3.4028235e38f));
-            nk = wk ? -nk : nk;
-            nm = wm ? -nm : nm;
-          }
-          st[i] = make_float2(nk, nm);
+          worst = max(worst, max(__float_as_uint(pw[i].x), __float_as_uint(pw[i].y)));
         });
+        P2 v[16];                             // X^ of (frame A, frame B)
+        if (cur.kind != 1 && !__any_sync(0xffffffffu, worst >= 0x7f800000u)) {
+          static_for<0, 16>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const float a_ = fmaf(x.tau, st[i], sqrt_ftz(pw[i].x) * x.mscale);
+            const float b_ = fmaf(x.tau, a_, sqrt_ftz(pw[i].y) * x.mscale);
+            v[i] = P2(a_, b_);
+            st[i] = has_b ? b_ : a_;
+          });
+        } else {
+          static_for<0, 16>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const float a0 = fmaf(x.tau, fabsf(st[i]), sqrt_ftz(pw[i].x) * x.mscale), a_ = finite_or_zero(a0);
+            const float b0 = fmaf(x.tau, a_, sqrt_ftz(pw[i].y) * x.mscale), b_ = finite_or_zero(b0);
+            v[i] = P2(a_, b_);
+            float n_ = has_b ? b_ : a_;
+            if (cur.kind == 1) {   // aggregate pass: remember in the sign that the bin was wiped inside this segment
+              const bool wiped = signbit(st[i]) || !(fabsf(a0) <= 3.4028235e38f) || (has_b && !(fabsf(b0) <= 3.4028235e38f));
+              n_ = wiped ? -n_ : n_;
+            }
+            st[i] = n_;
+          });
+        }
         // ---- epilogue: X^ -> dB / byte / colour of both frames (nothing to write in the aggregate pass)
         if (cur.kind != 1) {
           const int ta = cur.f0 + 2 * p;
           T* __restrict__ row_a = out + ((long long)cur.clip * x.out_clip_rows + ta) * (long long)kW32M;
           T* __restrict__ row_b = row_a + kW32M;
           if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
-            uint16_t* sb16 = s_stage + (q & 1) * 1024;
             const P2 scale = bc(2.f * ep.byte_a);
-            static_for<0, 8>([&](auto ii) {
+            static_for<0, 16>([&](auto ii) {
               constexpr int i = decltype(ii)::value;
-              const int k = lane + 32 * (i0 + i);
-              int mk = kW32M - k;
-              if (i0 + i == 0 && lane0) mk = 512;
-              const P2 bk = fma2(P2(lg2_ftz(vk[i].v.x), lg2_ftz(vk[i].v.y)), scale, bc(ep.byte_b0));
-              const P2 bm = fma2(P2(lg2_ftz(vm[i].v.x), lg2_ftz(vm[i].v.y)), scale, bc(ep.byte_b0));
-              const unsigned ka = byte_of_scaled(bk.v.x), kb = byte_of_scaled(bk.v.y);
-              const unsigned ma = byte_of_scaled(bm.v.x), mb = byte_of_scaled(bm.v.y);
+              const int bin = xs_bin(i, lane, c);
+              const P2 bv = fma2(P2(lg2_ftz(v[i].v.x), lg2_ftz(v[i].v.y)), scale, bc(ep.byte_b0));
+              const unsigned ba = byte_of_scaled(bv.v.x), bb = byte_of_scaled(bv.v.y);
               if constexpr (OUT == kOutU8) {
-                sb16[k] = (uint16_t)__byte_perm(ka, kb, 0x0040);
-                sb16[mk] = (uint16_t)__byte_perm(ma, mb, 0x0040);
+                sb16[bin & 511] = (uint16_t)__byte_perm(ba, bb, 0x0040);
               } else {
-                row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
-                if (has_b) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
+                row_a[bin] = __ldg(ep.lut + ba);
+                if (has_b) row_b[bin] = __ldg(ep.lut + bb);
               }
             });
             if constexpr (OUT == kOutU8) {
-              // both consumers have staged their bins; each stores half of the two rows (8-byte coalesced).  The stage
-              // is double buffered: this barrier also tells the other consumer that the stage of pair q - 1 is free.
-              asm volatile("bar.sync 13, 64;" ::: "memory");
+              __syncwarp();
               const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
-              uint2* ra = reinterpret_cast<uint2*>(row_a);
-              uint2* rb = reinterpret_cast<uint2*>(row_b);
+              uint2* ra = reinterpret_cast<uint2*>(row_a) + c * 64;
+              uint2* rb = reinterpret_cast<uint2*>(row_b) + c * 64;
 #pragma unroll
-              for (int cc = 2 * c; cc < 2 * c + 2; ++cc) {
+              for (int cc = 0; cc < 2; ++cc) {
                 const uint4 wv = s16[cc * 32 + lane];
                 ra[cc * 32 + lane] = make_uint2(__byte_perm(wv.x, wv.y, 0x6420), __byte_perm(wv.z, wv.w, 0x6420));
                 if (has_b) rb[cc * 32 + lane] = make_uint2(__byte_perm(wv.x, wv.y, 0x7531), __byte_perm(wv.z, wv.w, 0x7531));
               }
+              __syncwarp();
             }
           } else {
-            static_for<0, 8>([&](auto ii) {
+            static_for<0, 16>([&](auto ii) {
               constexpr int i = decltype(ii)::value;
-              const int k = lane + 32 * (i0 + i);
-              int mk = kW32M - k;
-              if (i0 + i == 0 && lane0) mk = 512;
-              P2 fk = vk[i], fm = vm[i];
-              if constexpr (OUT == kOutF32Db) {
-                fk = mul2(P2(lg2_ftz(fk.v.x), lg2_ftz(fk.v.y)), bc(2.f * ep.db_scale));
-                fm = mul2(P2(lg2_ftz(fm.v.x), lg2_ftz(fm.v.y)), bc(2.f * ep.db_scale));
-              }
-              row_a[k] = fk.v.x; row_a[mk] = fm.v.x;
-              if (has_b) { row_b[k] = fk.v.y; row_b[mk] = fm.v.y; }
+              const int bin = xs_bin(i, lane, c);
+              P2 f = v[i];
+              if constexpr (OUT == kOutF32Db) f = mul2(P2(lg2_ftz(f.v.x), lg2_ftz(f.v.y)), bc(2.f * ep.db_scale));
+              row_a[bin] = f.v.x;
+              if (has_b) row_b[bin] = f.v.y;
             });
           }
         }
-        ++q;
       }
       // ---- last pair of the work item done: hand the state to the next segment (or to the caller)
       if (!(cur.kind == 2 && cur.seg + 1 < x.segs)) {
         if (cur.seg + 1 < x.segs) {
           const long long me = (long long)cur.seg * x.n_clips + cur.clip;
-          float2* __restrict__ cv = x.carry + me * 512 + i0 * 32 + lane;
-          static_for<0, 8>([&](auto ii) { constexpr int i = decltype(ii)::value; cv[i * 32] = st[i]; });
+          float* __restrict__ cv = reinterpret_cast<float*>(x.carry) + (me * 2 + c) * 512 + lane;
+          static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; cv[i * 32] = st[i]; });
           __threadfence();
           __syncwarp();
           if (lane0) st_release_u32(x.flags + 2 * me + c, x.epoch);
         } else if (cur.kind != 1 && x.state_out != nullptr) {
           float* __restrict__ so = x.state_out + (long long)cur.clip * kW32M;
-          static_for<0, 8>([&](auto ii) {
-            constexpr int i = decltype(ii)::value;
-            so[xs_bin(i0 + i, lane, 0)] = st[i].x;
-            so[xs_bin(i0 + i, lane, 1) & (kW32M - 1)] = st[i].y;
-          });
+          static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; so[xs_bin(i, lane, c) & (kW32M - 1)] = st[i]; });
         }
       }
     }
@@ -395,7 +390,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     }
 
     // ---- untangle (kernel_w32x2p.cuh): mirrors fetched in place by shuffle, then 16 register steps; each step's
-    //      four powers (A and B at the bin, A and B at its mirror) go to the planes as one 16-byte store
+    //      powers (frames A and B at the bin, A and B at its mirror) go to the planes as two 8-byte stores
     const P2 p512 = mul2(bc(4.f), fma2(a[16].re, a[16].re, mul2(a[16].im, a[16].im)));
     static_for<0, 16>([&](auto ii) {
       constexpr int i = 15 - decltype(ii)::value;
@@ -421,7 +416,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       const P2 qk = fma2(xr, xr, mul2(xi, xi));
       P2 qm = fma2(yr, yr, mul2(yi, yi));
       if constexpr (i == 0) qm = P2(lane0 ? p512.v.x : qm.v.x, lane0 ? p512.v.y : qm.v.y);
-      xp[i * 32 + lane] = make_float4(qk.v.x, qk.v.y, qm.v.x, qm.v.y);
+      reinterpret_cast<float2*>(xp)[i * 32 + lane] = qk.v;          // plane 0: the bins this lane computes directly
+      reinterpret_cast<float2*>(xp)[512 + i * 32 + lane] = qm.v;    // plane 1: their mirrors
       static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
         constexpr int m = decltype(mm)::value;
         s[m] = ldg_nc_f2(nsrc + 32 * m);
