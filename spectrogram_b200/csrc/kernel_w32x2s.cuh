@@ -1,30 +1,22 @@
 // n_fft = 2048 with smoothingTimeConstant > 0 in ONE pass: the frame-pair kernel of kernel_w32x2p.cuh with the
 // AnalyserNode recurrence  X^_t[k] = tau X^_{t-1}[k] + (1 - tau) |X_t[k]|  (3D/visualizer.js:351,357,362 set tau per
-// mode; [SPEC] step 4) applied on chip between the untangle and the dB / byte epilogue.  No magnitude scratch in HBM.
+// mode; [SPEC] step 4) fused between the untangle and the dB / byte epilogue.  No magnitude scratch in HBM.
 //
-// The FFTs of a clip's frames are independent; only the recurrence is ordered.  A CTA owns a SEGMENT of consecutive
-// frames of one clip and its warps are specialised:
-//   producers (10 warps)  take the segment's frame pairs round robin and run loader -> window -> FFT -> untangle exactly
-//                         as kernel_w32x2p.cuh, but instead of an epilogue they leave the pair's powers |2X|^2 in their
-//                         own (now idle) exchange planes, 16 x STS.128 per lane, and signal a "full" mbarrier;
-//   consumers (2 warps)   walk the pairs IN ORDER; consumer c owns state slots 8c .. 8c+7 of every lane (slot (i, lane)
-//                         = bins lane + 32 i and its mirror) and keeps X^ of those 512 bins in registers for the whole
-//                         segment: wait full, 8 x LDS.128, release the planes ("empty" mbarrier), sqrt, two FMAs per
-//                         value, lg2, byte, staged row stores.  A consumer needs a fraction of the time the producers
-//                         take to deliver a pair, so the ordered part does not throttle the FFTs, and a producer only
-//                         waits if its previous pair has not been read by the time it reaches its next exchange.
-// (A first version passed the state update itself from warp to warp through an mbarrier chain, every warp doing its own
-//  epilogue: 472 M frames/s with 8 warps, 395 M with 12 -- the ring of turns makes every warp wait for the slowest.)
-// Segments of one clip are chained through a carry vector in global memory (per consumer half, with a ready flag):
+// The FFTs of a clip's frames are independent; only the recurrence is ordered.  So a CTA owns a SEGMENT of consecutive
+// frames of one clip, its 12 warps take the segment's frame pairs round robin and run window -> FFT -> untangle -> sqrt
+// concurrently, and only the state update -- 16 x (LDS.64, 4 FMA, STS.64) per lane, ~250 cycles -- is passed from warp
+// to warp in pair order through an mbarrier chain (the waiting warp sleeps in try_wait, it takes no issue slots).  X^
+// of the segment lives in 4 KB of shared memory in lane order (slot (i, lane) = bins lane + 32 i and its mirror).
+// Segments of one clip are chained through a carry vector in global memory:
 //   mode 0 (chain)  many clips: tasks (segment, clip) are dealt to CTAs segment-major, so a task's predecessor was
-//                   started ~n_clips / gridDim tasks earlier.  Exactly the sequential arithmetic, bit for bit.
+//                   started ~n_clips / gridDim tasks earlier; its last pair publishes the state and a flag, the
+//                   successor's first pair waits for it.  Exactly the sequential arithmetic, bit for bit.
 //   mode 1 (few)    fewer clips than CTAs: one task per CTA, run twice -- first without output from a zero state,
 //                   which yields the segment's aggregate (the recurrence is linear), then, after a look-back over the
 //                   aggregates of the segments before it (all produced concurrently), again from the true state with
 //                   output.  Twice the arithmetic, on a GPU that would otherwise idle; one launch.
-// [SPEC] "non-finite X^ -> 0" is applied per value; in the aggregate pass the sign bit of a state value records that
-// a non-finite frame wiped that bin inside the segment (X^ itself is never negative), so the look-back drops what
-// came in from earlier segments.
+// [SPEC] "non-finite X^ -> 0" is applied per frame: one integer max over the lane's magnitudes per pair decides
+// whether the slow, per-value path is needed.
 #pragma once
 #include "kernel_w32x2p.cuh"
 
@@ -33,23 +25,24 @@ namespace sg {
 struct XsGeom {
   long long n_clips;
   long long out_clip_rows;  // output rows between consecutive clips (>= frames_per_clip: a frame range of longer clips)
-  int seg_frames;           // frames per segment (even); the last segment of a clip may be shorter
-  int segs;                 // segments per clip
+  int seg_frames;          // frames per segment (even); the last segment of a clip may be shorter
+  int segs;                // segments per clip
   float tau;
-  float mscale;             // (1 - tau) / norm: sqrt(|2X|^2) * mscale = (1 - tau) |X| / N
-  float dec;                // tau^seg_frames (mode 1 look-back)
-  const float* state_in;    // [n_clips][1024], natural bin order; nullptr = zeros
-  float* state_out;         // [n_clips][1024], natural bin order; nullptr = not wanted
-  float2* carry;            // [segs * n_clips][16][32]: state at the END of a segment (mode 1: its aggregate)
-  unsigned* flags;          // [segs * n_clips][2]: == epoch once consumer c's half of the carry is visible
+  float mscale;            // (1 - tau) / norm: sqrt(|2X|^2) * mscale = (1 - tau) |X| / N
+  float dec;               // tau^seg_frames (mode 1 look-back)
+  const float* state_in;   // [n_clips][1024], natural bin order; nullptr = zeros
+  float* state_out;        // [n_clips][1024], natural bin order; nullptr = not wanted
+  float2* carry;           // [segs * n_clips][16][32]: state at the END of a segment (mode 1: its aggregate)
+  unsigned* flags;         // [segs * n_clips]: == epoch once the carry is visible
   unsigned epoch;
   int mode;
 };
 
-constexpr int kXsProducers = 10, kXsConsumers = 2, kXsWarps = kXsProducers + kXsConsumers;
-constexpr int kXsStageBytes = 2 * 1024;                                // per consumer: 512 (A, B) byte pairs
-constexpr int kXsSmemBytes = kXpTableBytes + kXsStageBytes + 2 * kXsProducers * 8 + kXsProducers * kXpWarpBytes;
-constexpr int kXsMaxRegs = (65536 / (kXsWarps * 32)) / 8 * 8;
+constexpr int kXsStateBytes = 16 * 32 * 8;
+template <int NW>
+struct XsShape {
+  static constexpr int kSmemBytes = XpShape<NW>::kSmemBytes + kXsStateBytes + 4 * NW * 8;   // up to 4 turn chains
+};
 
 // the work item a pair belongs to: (segment, clip) and what to do at its first / last pair
 struct XsItem {
@@ -91,21 +84,22 @@ __device__ __forceinline__ int xs_bin(int i, int lane, int half) {
   return half == 0 ? k : ((i == 0 && lane == 0) ? 512 : kW32M - k);
 }
 
-template <int OUT, int HOPJ>
-__global__ void __launch_bounds__(kXsWarps * 32, 1)
+// LATE: the next pair's loads are issued after the turn has been passed on (in the epilogue) instead of inside the untangle
+template <int OUT, int NW, int HOPJ, bool LATE, int K, bool NOSYNC = false>
+__global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
-  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ, NP = kXsProducers;
+  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ;
   extern __shared__ float4 smem_raw[];
   float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
   float2* s_ut = s_twb + 5 * 32;                                       // [16][32] W_2048^{lane + 32 i}
-  uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_ut + 16 * 32);     // [2][512] (A, B) byte pairs, one stage per consumer
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + 2 * 512);  // [NP] producer w's powers are in its planes
-  uint64_t* s_empty = s_full + NP;                                     // [NP] both consumers have read them
-  unsigned char* planes = reinterpret_cast<unsigned char*>(s_empty + NP);
+  float2* s_state = s_ut + 16 * 32;                                    // [16][32] (X^[k], X^[mirror k])
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_state + 16 * 32);    // [K][NW] the turn of warp w on slot group c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool lane0 = lane == 0;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(s_bar + 4 * NW) + warp * kXpWarpBytes;
+  float4* xp = reinterpret_cast<float4*>(wbase);                       // exchange planes
+  uint16_t* sb16 = reinterpret_cast<uint16_t*>(wbase);                 // byte stage: aliases the planes
 
   {
     const float2* w2 = reinterpret_cast<const float2*>(pl.win);
@@ -119,153 +113,13 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       s_twb[i] = __ldg(pl.tw2 + ((1 << u) - 1) * 32 + l);
     }
     for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) s_ut[i] = __ldg(pl.ut + i);
-    if (threadIdx.x < NP) {
-      mbar_init(s_full + threadIdx.x, 1);
-      mbar_init(s_empty + threadIdx.x, kXsConsumers);
-    }
+    if (threadIdx.x < K * NW) mbar_init(s_bar + threadIdx.x, 1);
   }
   __syncthreads();
+  if (threadIdx.x < K) mbar_arrive(s_bar + threadIdx.x * NW);      // warp 0 holds the first turn of every group
+  unsigned turn = 0;                             // phase parity of this warp's next wait
+
   const int fpc = (int)g.frames_per_clip;
-
-  if (warp >= NP) {
-    // =================================================================================== consumer
-    // consumer 0 owns the bins a lane computes directly (k = lane + 32 i < 512), consumer 1 their mirrors (bins 513 ..
-    // 1023, and bin 512 in lane 0's slot 0): each keeps X^ of its 512 bins in registers and writes its half of the rows
-    const int c = warp - NP;
-    uint16_t* sb16 = s_stage + c * 512;     // this consumer's byte stage: 512 (A, B) pairs
-    float st[16];                           // X^ of this consumer's bins: slot i of every lane
-    unsigned full_par = 0;
-    int w = 0;                              // producer that delivers the current pair
-    for (XsItem cur = xs_item(x, fpc, 0); cur.valid; cur = xs_item(x, fpc, cur.it + 1)) {
-      const int npairs = (cur.nfr + 1) / 2;
-      // ---- first pair of a work item: the state the segment starts from
-      {
-        const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
-        static_for<0, 16>([&](auto ii) {
-          constexpr int i = decltype(ii)::value;
-          st[i] = si ? si[xs_bin(i, lane, c) & (kW32M - 1)] : 0.f;
-        });
-        if (cur.kind != 1 && cur.seg > 0) {
-          // chain: the previous segment's final state; look-back: Horner over the aggregates of all earlier segments,
-          // state = dec^s state_in + sum_{j < s} dec^(s-1-j) aggregate_j (an aggregate with its sign set wipes the rest)
-          for (int j = cur.kind == 0 ? cur.seg - 1 : 0; j < cur.seg; ++j) {
-            const long long tj = (long long)j * x.n_clips + cur.clip;
-            if (lane0) while (ld_acquire_u32(x.flags + 2 * tj + c) != x.epoch) {}
-            __syncwarp();
-            const float* __restrict__ cv = reinterpret_cast<const float*>(x.carry) + (tj * 2 + c) * 512 + lane;
-            static_for<0, 16>([&](auto ii) {
-              constexpr int i = decltype(ii)::value;
-              const float v = __ldcg(cv + i * 32);
-              if (cur.kind == 0) st[i] = v;
-              else st[i] = fmaf(signbit(v) ? 0.f : x.dec, st[i], fabsf(v));
-            });
-          }
-        }
-      }
-      for (int p = 0; p < npairs; ++p) {
-        const bool has_b = 2 * p + 1 < cur.nfr;
-        // ---- the pair's powers from producer w's planes
-        while (!mbar_try_wait(s_full + w, full_par)) {}
-        const float2* __restrict__ src = reinterpret_cast<const float2*>(planes + w * kXpWarpBytes) + c * 512 + lane;
-        float2 pw[16];
-        static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; pw[i] = src[i * 32]; });
-        __syncwarp();
-        if (lane0) mbar_arrive(s_empty + w);
-        if (++w == NP) { w = 0; full_par ^= 1; }
-        // ---- the recurrence for frames A then B.  [SPEC] a non-finite X^ is set to 0: one integer max over the
-        //      lane's powers decides whether the per-value path is needed (Inf and NaN have the largest bit patterns)
-        unsigned worst = 0;
-        static_for<0, 16>([&](auto ii) {
-          constexpr int i = decltype(ii)::value;
-          worst = max(worst, max(__float_as_uint(pw[i].x), __float_as_uint(pw[i].y)));
-        });
-        P2 v[16];                             // X^ of (frame A, frame B)
-        if (cur.kind != 1 && !__any_sync(0xffffffffu, worst >= 0x7f800000u)) {
-          static_for<0, 16>([&](auto ii) {
-            constexpr int i = decltype(ii)::value;
-            const float a_ = fmaf(x.tau, st[i], sqrt_ftz(pw[i].x) * x.mscale);
-            const float b_ = fmaf(x.tau, a_, sqrt_ftz(pw[i].y) * x.mscale);
-            v[i] = P2(a_, b_);
-            st[i] = has_b ? b_ : a_;
-          });
-        } else {
-          static_for<0, 16>([&](auto ii) {
-            constexpr int i = decltype(ii)::value;
-            const float a0 = fmaf(x.tau, fabsf(st[i]), sqrt_ftz(pw[i].x) * x.mscale), a_ = finite_or_zero(a0);
-            const float b0 = fmaf(x.tau, a_, sqrt_ftz(pw[i].y) * x.mscale), b_ = finite_or_zero(b0);
-            v[i] = P2(a_, b_);
-            float n_ = has_b ? b_ : a_;
-            if (cur.kind == 1) {   // aggregate pass: remember in the sign that the bin was wiped inside this segment
-              const bool wiped = signbit(st[i]) || !(fabsf(a0) <= 3.4028235e38f) || (has_b && !(fabsf(b0) <= 3.4028235e38f));
-              n_ = wiped ? -n_ : n_;
-            }
-            st[i] = n_;
-          });
-        }
-        // ---- epilogue: X^ -> dB / byte / colour of both frames (nothing to write in the aggregate pass)
-        if (cur.kind != 1) {
-          const int ta = cur.f0 + 2 * p;
-          T* __restrict__ row_a = out + ((long long)cur.clip * x.out_clip_rows + ta) * (long long)kW32M;
-          T* __restrict__ row_b = row_a + kW32M;
-          if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
-            const P2 scale = bc(2.f * ep.byte_a);
-            static_for<0, 16>([&](auto ii) {
-              constexpr int i = decltype(ii)::value;
-              const int bin = xs_bin(i, lane, c);
-              const P2 bv = fma2(P2(lg2_ftz(v[i].v.x), lg2_ftz(v[i].v.y)), scale, bc(ep.byte_b0));
-              const unsigned ba = byte_of_scaled(bv.v.x), bb = byte_of_scaled(bv.v.y);
-              if constexpr (OUT == kOutU8) {
-                sb16[bin & 511] = (uint16_t)__byte_perm(ba, bb, 0x0040);
-              } else {
-                row_a[bin] = __ldg(ep.lut + ba);
-                if (has_b) row_b[bin] = __ldg(ep.lut + bb);
-              }
-            });
-            if constexpr (OUT == kOutU8) {
-              __syncwarp();
-              const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
-              uint2* ra = reinterpret_cast<uint2*>(row_a) + c * 64;
-              uint2* rb = reinterpret_cast<uint2*>(row_b) + c * 64;
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const uint4 wv = s16[cc * 32 + lane];
-                ra[cc * 32 + lane] = make_uint2(__byte_perm(wv.x, wv.y, 0x6420), __byte_perm(wv.z, wv.w, 0x6420));
-                if (has_b) rb[cc * 32 + lane] = make_uint2(__byte_perm(wv.x, wv.y, 0x7531), __byte_perm(wv.z, wv.w, 0x7531));
-              }
-              __syncwarp();
-            }
-          } else {
-            static_for<0, 16>([&](auto ii) {
-              constexpr int i = decltype(ii)::value;
-              const int bin = xs_bin(i, lane, c);
-              P2 f = v[i];
-              if constexpr (OUT == kOutF32Db) f = mul2(P2(lg2_ftz(f.v.x), lg2_ftz(f.v.y)), bc(2.f * ep.db_scale));
-              row_a[bin] = f.v.x;
-              if (has_b) row_b[bin] = f.v.y;
-            });
-          }
-        }
-      }
-      // ---- last pair of the work item done: hand the state to the next segment (or to the caller)
-      if (!(cur.kind == 2 && cur.seg + 1 < x.segs)) {
-        if (cur.seg + 1 < x.segs) {
-          const long long me = (long long)cur.seg * x.n_clips + cur.clip;
-          float* __restrict__ cv = reinterpret_cast<float*>(x.carry) + (me * 2 + c) * 512 + lane;
-          static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; cv[i * 32] = st[i]; });
-          __threadfence();
-          __syncwarp();
-          if (lane0) st_release_u32(x.flags + 2 * me + c, x.epoch);
-        } else if (cur.kind != 1 && x.state_out != nullptr) {
-          float* __restrict__ so = x.state_out + (long long)cur.clip * kW32M;
-          static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; so[xs_bin(i, lane, c) & (kW32M - 1)] = st[i]; });
-        }
-      }
-    }
-    return;
-  }
-
-  // ===================================================================================== producer
-  float4* xp = reinterpret_cast<float4*>(planes + warp * kXpWarpBytes);   // exchange planes, then the pair's powers
   // pairs with t in [t_lo, t_hi] lie wholly inside their clip (no zero fill)
   int t_lo, t_hi;
   {
@@ -281,17 +135,18 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     const int t = c.f0 + 2 * p;
     return c.valid && 2 * p + 1 < c.nfr && t >= t_lo && t <= t_hi && ((pcm_lo + ((unsigned)off << 2)) & 7u) == 0;
   };
-  // the pair NP places further down this CTA's pair sequence.  Only (item index, pair index) is carried from one
-  // iteration to the next; the item's fields are re-derived where they are needed.
+  // the pair NW places further down this CTA's pair sequence.  Only (item index, pair index) is carried from one
+  // iteration to the next; the item's fields are re-derived where they are needed (registers are what this kernel
+  // has least of).
   auto advance = [&](XsItem& c, int& p) {
-    p += NP;
+    p += NW;
     while (c.valid && p >= (c.nfr + 1) / 2) {
       p -= (c.nfr + 1) / 2;
       c = xs_item(x, fpc, c.it + 1);
     }
   };
 
-  int it, p = warp - NP;
+  int it, p = warp - NW;
   bool cur_fast;
   {
     XsItem c0 = xs_item(x, fpc, 0);
@@ -301,7 +156,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     cur_fast = pair_fast(c0, p, pair_off(c0, p));
   }
   const int partner = (32 - lane) & 31;
-  unsigned empty_par = 1;       // a fresh mbarrier reads as "the phase before has completed": the planes start free
+  const bool lane0 = lane == 0;
 
   float2 s[NLOAD];
   const float2* idle_src = reinterpret_cast<const float2*>(pl.win) + lane;   // 4096 readable floats (build_plan)
@@ -313,6 +168,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
 
   while (true) {
     const XsItem cur = xs_item(x, fpc, it);
+    const int ta = cur.f0 + 2 * p;
+    const bool has_b = 2 * p + 1 < cur.nfr;
     // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
     C2 a[32];
     if (cur_fast) {
@@ -326,7 +183,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     } else {
       // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
       const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
-      const long long start_a = g.start0 + (long long)(cur.f0 + 2 * p) * HOP, start_b = start_a + (2 * p + 1 < cur.nfr ? HOP : 0);
+      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
       auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xa + q) : 0.f; };
       static_for<0, 16>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
@@ -346,9 +203,6 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     dit2_stage_const<3>(a);
     dit2_stage_const<4>(a);
     dit2_stage_const<5>(a);
-    // the planes still hold the previous pair's powers until both consumers have read them
-    while (!mbar_try_wait(s_empty + warp, empty_par)) {}
-    empty_par ^= 1;
     {
       float2* wre = reinterpret_cast<float2*>(xp) + ((lane >> 1) * kXpStride) * 2 + (lane & 1);
       float2* wim = wre + 16 * kXpStride * 2;
@@ -389,8 +243,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       nsrc = nxt_fast ? reinterpret_cast<const float2*>(g.pcm + nxt_off) + lane : idle_src;
     }
 
-    // ---- untangle (kernel_w32x2p.cuh): mirrors fetched in place by shuffle, then 16 register steps; each step's
-    //      powers (frames A and B at the bin, A and B at its mirror) go to the planes as two 8-byte stores
+    // ---- untangle (kernel_w32x2p.cuh): mirrors fetched in place by shuffle, then 16 register steps
     const P2 p512 = mul2(bc(4.f), fma2(a[16].re, a[16].re, mul2(a[16].im, a[16].im)));
     static_for<0, 16>([&](auto ii) {
       constexpr int i = 15 - decltype(ii)::value;
@@ -402,6 +255,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
       a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
     });
+    P2 pk[16], pm[16];
+    unsigned worst = 0;   // largest bit pattern among this lane's powers: >= 0x7f800000 means Inf or NaN
     static_for<0, 16>([&](auto ii) {
       constexpr int i = decltype(ii)::value;
       const P2 zmr = a[31 - i].re, zmi = a[31 - i].im;
@@ -413,18 +268,185 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       const P2 xi = fma2(ox, bc(w.y), fma2(oy, bc(w.x), ey));
       const P2 yr = fma2(ex, bc(2.f), neg(xr));                            // 2 conj X[1024-k]
       const P2 yi = fma2(ey, bc(2.f), neg(xi));
-      const P2 qk = fma2(xr, xr, mul2(xi, xi));
-      P2 qm = fma2(yr, yr, mul2(yi, yi));
+      P2 qk = fma2(xr, xr, mul2(xi, xi)), qm = fma2(yr, yr, mul2(yi, yi));
       if constexpr (i == 0) qm = P2(lane0 ? p512.v.x : qm.v.x, lane0 ? p512.v.y : qm.v.y);
-      reinterpret_cast<float2*>(xp)[i * 32 + lane] = qk.v;          // plane 0: the bins this lane computes directly
-      reinterpret_cast<float2*>(xp)[512 + i * 32 + lane] = qm.v;    // plane 1: their mirrors
-      static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
-        constexpr int m = decltype(mm)::value;
-        s[m] = ldg_nc_f2(nsrc + 32 * m);
-      });
+      worst = max(max(worst, max(__float_as_uint(qk.v.x), __float_as_uint(qk.v.y))),
+                  max(__float_as_uint(qm.v.x), __float_as_uint(qm.v.y)));
+      // (1 - tau) |X| / N of both frames
+      pk[i] = mul2(P2(sqrt_ftz(qk.v.x), sqrt_ftz(qk.v.y)), bc(x.mscale));
+      pm[i] = mul2(P2(sqrt_ftz(qm.v.x), sqrt_ftz(qm.v.y)), bc(x.mscale));
+      if constexpr (!LATE) {
+        static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
+          constexpr int m = decltype(mm)::value;
+          s[m] = ldg_nc_f2(nsrc + 32 * m);
+        });
+      }
     });
+    const bool dirty = __any_sync(0xffffffffu, worst >= 0x7f800000u);
+
+    // ---- the recurrence, in pair order.  The 16 state slots of a lane are cut into K groups with a turn of their
+    //      own each, so warp w + 1 updates group c while warp w is already on group c + 1: the ordered part of the
+    //      kernel is pipelined K deep.  In the aggregate pass (kind 1) the sign bit of a state value records that a
+    //      non-finite frame wiped that bin inside this segment (X^ itself is never negative): the look-back must
+    //      then drop what came in from earlier segments.
+    if (p == 0 && cur.kind != 1 && cur.seg > 0) {
+      // the segments this one starts from must have been published (chain: the previous one; look-back: all of them)
+      if (lane0) {
+        for (int j = cur.kind == 0 ? cur.seg - 1 : 0; j < cur.seg; ++j)
+          while (ld_acquire_u32(x.flags + (long long)j * x.n_clips + cur.clip) != x.epoch) {}
+      }
+      __syncwarp();
+    }
+    static_for<0, K>([&](auto cc) {
+      constexpr int c = decltype(cc)::value, i0 = c * (16 / K), i1 = i0 + 16 / K;
+      if constexpr (!NOSYNC) while (!mbar_try_wait(s_bar + c * NW + warp, turn)) {}
+      if (p == 0) {
+        // first pair of a work item: the state the segment starts from
+        const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
+        if (cur.kind == 1 || cur.seg == 0) {
+          static_for<i0, i1>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            s_state[i * 32 + lane] =
+                si ? make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
+          });
+        } else if (cur.kind == 0) {
+          const float2* __restrict__ cv = x.carry + ((long long)(cur.seg - 1) * x.n_clips + cur.clip) * 512 + lane;
+          static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = __ldcg(cv + i * 32); });
+        } else {
+          // look-back: state at the start of segment s = dec^s state_in + sum_{j < s} dec^(s-1-j) aggregate_j (Horner);
+          // an aggregate with its sign bit set wipes what came before it
+          float2 acc[16 / K];
+          static_for<i0, i1>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            acc[i - i0] = si ? make_float2(si[xs_bin(i, lane, 0)], si[xs_bin(i, lane, 1) & (kW32M - 1)]) : make_float2(0.f, 0.f);
+          });
+          for (int j = 0; j < cur.seg; ++j) {
+            const float2* __restrict__ cv = x.carry + ((long long)j * x.n_clips + cur.clip) * 512 + lane;
+            static_for<i0, i1>([&](auto ii) {
+              constexpr int i = decltype(ii)::value;
+              const float2 v = __ldcg(cv + i * 32);
+              acc[i - i0] = make_float2(fmaf(signbit(v.x) ? 0.f : x.dec, acc[i - i0].x, fabsf(v.x)),
+                                        fmaf(signbit(v.y) ? 0.f : x.dec, acc[i - i0].y, fabsf(v.y)));
+            });
+          }
+          static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = acc[i - i0]; });
+        }
+        __syncwarp();
+      }
+      if (!dirty && cur.kind != 1) {
+        static_for<i0, i1>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          const float2 st = s_state[i * 32 + lane];
+          const float ka = fmaf(x.tau, st.x, pk[i].v.x), kb = fmaf(x.tau, ka, pk[i].v.y);
+          const float ma = fmaf(x.tau, st.y, pm[i].v.x), mb = fmaf(x.tau, ma, pm[i].v.y);
+          pk[i] = P2(ka, kb);
+          pm[i] = P2(ma, mb);
+          s_state[i * 32 + lane] = has_b ? make_float2(kb, mb) : make_float2(ka, ma);
+        });
+      } else {
+        static_for<i0, i1>([&](auto ii) {   // [SPEC] a non-finite X^ is set to 0 (and, kind 1, remembered in the sign)
+          constexpr int i = decltype(ii)::value;
+          const float2 st = s_state[i * 32 + lane];
+          const float ka0 = fmaf(x.tau, fabsf(st.x), pk[i].v.x), ka = finite_or_zero(ka0);
+          const float kb0 = fmaf(x.tau, ka, pk[i].v.y), kb = finite_or_zero(kb0);
+          const float ma0 = fmaf(x.tau, fabsf(st.y), pm[i].v.x), ma = finite_or_zero(ma0);
+          const float mb0 = fmaf(x.tau, ma, pm[i].v.y), mb = finite_or_zero(mb0);
+          pk[i] = P2(ka, kb);
+          pm[i] = P2(ma, mb);
+          float nk = has_b ? kb : ka, nm = has_b ? mb : ma;
+          if (cur.kind == 1) {
+            const bool wk = signbit(st.x) || !(fabsf(ka0) <= 3.4028235e38f) || (has_b && !(fabsf(kb0) <= 3.4028235e38f));
+            const bool wm = signbit(st.y) || !(fabsf(ma0) <= 3.4028235e38f) || (has_b && !(fabsf(mb0) <= 3.4028235e38f));
+            nk = wk ? -nk : nk;
+            nm = wm ? -nm : nm;
+            pk[i] = P2(nk, nk);     // no output in this pass: the registers only feed the carry-out below
+            pm[i] = P2(nm, nm);
+          }
+          s_state[i * 32 + lane] = make_float2(nk, nm);
+        });
+      }
+      __syncwarp();
+      if (lane0) mbar_arrive(s_bar + c * NW + (warp + 1 == NW ? 0 : warp + 1));
+    });
+    turn ^= 1;
+    const bool last = p == (cur.nfr + 1) / 2 - 1;
+    if (last && !(cur.kind == 2 && cur.seg + 1 < x.segs)) {
+      // last pair of a work item: hand the state to the next segment (or to the caller)
+      if (cur.seg + 1 < x.segs) {
+        const long long me = (long long)cur.seg * x.n_clips + cur.clip;
+        float2* __restrict__ c = x.carry + me * 512 + lane;
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          c[i * 32] = has_b ? make_float2(pk[i].v.y, pm[i].v.y) : make_float2(pk[i].v.x, pm[i].v.x);
+        });
+        __threadfence();
+        __syncwarp();
+        if (lane0) st_release_u32(x.flags + me, x.epoch);
+      } else if (cur.kind != 1 && x.state_out != nullptr) {
+        float* __restrict__ so = x.state_out + (long long)cur.clip * kW32M;
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          so[xs_bin(i, lane, 0)] = has_b ? pk[i].v.y : pk[i].v.x;
+          so[xs_bin(i, lane, 1) & (kW32M - 1)] = has_b ? pm[i].v.y : pm[i].v.x;
+        });
+      }
+    }
+    if constexpr (LATE) {
+      static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + 32 * m); });
+    }
+
+    // ---- epilogue: X^ -> dB / byte / colour of both frames (nothing to write in the aggregate pass)
+    if (cur.kind != 1) {
+      T* __restrict__ row_a = out + ((long long)cur.clip * x.out_clip_rows + ta) * (long long)kW32M;
+      T* __restrict__ row_b = row_a + kW32M;
+      if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
+        const P2 scale = bc(2.f * ep.byte_a);
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          const int k = lane + 32 * i;
+          int mk = kW32M - k;
+          if constexpr (i == 0) { if (lane0) mk = 512; }
+          const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), scale, bc(ep.byte_b0));
+          const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), scale, bc(ep.byte_b0));
+          const unsigned ka = byte_of_scaled(vk.v.x), kb = byte_of_scaled(vk.v.y);
+          const unsigned ma = byte_of_scaled(vm.v.x), mb = byte_of_scaled(vm.v.y);
+          if constexpr (OUT == kOutU8) {
+            sb16[k] = (uint16_t)__byte_perm(ka, kb, 0x0040);
+            sb16[mk] = (uint16_t)__byte_perm(ma, mb, 0x0040);
+          } else {
+            row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
+            if (has_b) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
+          }
+        });
+        if constexpr (OUT == kOutU8) {
+          __syncwarp();
+          const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
+          uint2* ra = reinterpret_cast<uint2*>(row_a);
+          uint2* rb = reinterpret_cast<uint2*>(row_b);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 w = s16[c * 32 + lane];
+            ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+            if (has_b) rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+          }
+        }
+      } else {
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          const int k = lane + 32 * i;
+          int mk = kW32M - k;
+          if constexpr (i == 0) { if (lane0) mk = 512; }
+          P2 vk = pk[i], vm = pm[i];
+          if constexpr (OUT == kOutF32Db) {
+            vk = mul2(P2(lg2_ftz(vk.v.x), lg2_ftz(vk.v.y)), bc(2.f * ep.db_scale));
+            vm = mul2(P2(lg2_ftz(vm.v.x), lg2_ftz(vm.v.y)), bc(2.f * ep.db_scale));
+          }
+          row_a[k] = vk.v.x; row_a[mk] = vm.v.x;
+          if (has_b) { row_b[k] = vk.v.y; row_b[mk] = vm.v.y; }
+        });
+      }
+    }
     __syncwarp();
-    if (lane0) mbar_arrive(s_full + warp);
     if (!has_next) break;
     it = nit;
     p = np;

@@ -507,7 +507,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
   if (pl.n_fft != sg::kW32N || (cfg.hop != 512 && cfg.hop != 256) || e->kernel_variant != 0) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
-  const int grid_max = e->sm_count, nw = sg::kXsProducers;
+  const int grid_max = e->sm_count, nw = 12;
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
@@ -549,7 +549,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     x.state_out = (float*)e->xs_state.p;
   }
   SG_TRY(e->xs_carry.reserve((size_t)tasks * 512 * sizeof(float2)));
-  if (2 * (size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
+  if ((size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
     SG_TRY(e->xs_flags.reserve(std::max<size_t>(4 * (size_t)tasks, 4096) * sizeof(unsigned)));
     SG_CUDA(cudaMemsetAsync(e->xs_flags.p, 0, e->xs_flags.cap, st));   // flags only ever hold epochs of earlier launches
   }
