@@ -308,10 +308,12 @@ def spectrogram(pcm: np.ndarray, cfg: Config, chromium_cast: bool = False):
     w = make_window(cfg.window, cfg.n_fft, cfg.custom_window)
     mags = np.empty((n_clips, f, bins), dtype=np.float64)
     for c in range(n_clips):
-        m = magnitudes(frame_matrix(x[c], cfg.n_fft, cfg.hop, cfg.align), w, chromium_cast)
-        m = np.where(np.isfinite(m), m, 0.0)
+        with np.errstate(invalid="ignore", over="ignore"):
+            m = magnitudes(frame_matrix(x[c], cfg.n_fft, cfg.hop, cfg.align), w, chromium_cast)
         if cfg.smoothing > 0.0:
-            m, _ = smooth(m, cfg.smoothing)
+            m, _ = smooth(m, cfg.smoothing)      # [SPEC] step 4: a non-finite X^ is set to 0 (the state restarts)
+        else:
+            m = np.where(np.isfinite(m), m, 0.0)
         mags[c] = m
     return finish(mags, cfg)
 

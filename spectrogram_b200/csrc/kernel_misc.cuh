@@ -13,6 +13,9 @@ namespace sg {
 // the initial X^ and written back with the final one (so chunks of one clip can be chained, and
 // the streaming objects keep it across calls).  Arithmetic as Chromium: double, stored as float.
 // HBM-bound: 4 B read + elem B written per (frame, bin); coalesced across bins.
+// A non-finite magnitude (a frame with NaN / Inf samples, or |X|^2 overflowing float) enters the recurrence as 0 in
+// this two-kernel path -- the time-parallel form below needs finite inputs to stay linear -- so X^ decays over such a
+// frame; the fused kernel (kernel_w32x2s.cuh) applies [SPEC]'s "non-finite X^ -> 0" literally and restarts from 0.
 template <int OUT>
 __global__ void __launch_bounds__(256)
 smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* __restrict__ out,
@@ -30,7 +33,7 @@ smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
   for (; t + 4 <= frames; t += 4) {
     float v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(m + (t + u) * bins);
+    for (int u = 0; u < 4; ++u) v[u] = finite_or_zero(__ldg(m + (t + u) * bins));
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       s = finite_or_zero((float)(tau * (double)s + k1 * (double)v[u]));
@@ -38,7 +41,7 @@ smooth_emit_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
     }
   }
   for (; t < frames; ++t) {
-    s = finite_or_zero((float)(tau * (double)s + k1 * (double)__ldg(m + t * bins)));
+    s = finite_or_zero((float)(tau * (double)s + k1 * (double)finite_or_zero(__ldg(m + t * bins))));
     o[t * bins] = emit_mag<OUT>(s, ep);
   }
   state[idx] = s;
@@ -87,11 +90,11 @@ smooth_scan_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
     for (; t + 8 <= t1; t += 8) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
+      for (int u = 0; u < 8; ++u) v[u] = finite_or_zero(__ldg(m + (t + u) * bins));
 #pragma unroll
       for (int u = 0; u < 8; ++u) s = tau * s + k1 * (double)v[u];
     }
-    for (; t < t1; ++t) s = tau * s + k1 * (double)__ldg(m + t * bins);
+    for (; t < t1; ++t) s = tau * s + k1 * (double)finite_or_zero(__ldg(m + t * bins));
     carry[(clip * bins + b) * n_chunks + j] = (float)s;
   }
   grid.sync();
@@ -134,7 +137,7 @@ smooth_scan_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
     for (; t + 8 <= t1; t += 8) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(m + (t + u) * bins);
+      for (int u = 0; u < 8; ++u) v[u] = finite_or_zero(__ldg(m + (t + u) * bins));
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         s = finite_or_zero((float)(tau * (double)s + k1 * (double)v[u]));
@@ -142,7 +145,7 @@ smooth_scan_kernel(const float* __restrict__ mags, typename OutElem<OUT>::type* 
       }
     }
     for (; t < t1; ++t) {
-      s = finite_or_zero((float)(tau * (double)s + k1 * (double)__ldg(m + t * bins)));
+      s = finite_or_zero((float)(tau * (double)s + k1 * (double)finite_or_zero(__ldg(m + t * bins))));
       o[t * bins] = emit_mag<OUT>(s, ep);
     }
     if (j == n_chunks - 1) state[clip * bins + b] = s;

@@ -3,10 +3,10 @@
 // mode; [SPEC] step 4) fused between the untangle and the dB / byte epilogue.  No magnitude scratch in HBM.
 //
 // The FFTs of a clip's frames are independent; only the recurrence is ordered.  So a CTA owns a SEGMENT of consecutive
-// frames of one clip, its 12 warps take the segment's frame pairs round robin and run window -> FFT -> untangle -> sqrt
-// concurrently, and only the state update -- 16 x (LDS.64, 4 FMA, STS.64) per lane, ~250 cycles -- is passed from warp
-// to warp in pair order through an mbarrier chain (the waiting warp sleeps in try_wait, it takes no issue slots).  X^
-// of the segment lives in 4 KB of shared memory in lane order (slot (i, lane) = bins lane + 32 i and its mirror).
+// frames of one clip, its warps take the segment's frame pairs round robin and run window -> FFT -> untangle -> sqrt
+// concurrently, and only the state update -- 16 x (LDS.64, 4 FMA, STS.64) per lane -- is passed from warp to warp in
+// pair order through an mbarrier chain (the waiting warp sleeps in try_wait, it takes no issue slots).  X^ of the
+// segment lives in 4 KB of shared memory in lane order (slot (i, lane) = bins lane + 32 i and its mirror).
 // Segments of one clip are chained through a carry vector in global memory:
 //   mode 0 (chain)  many clips: tasks (segment, clip) are dealt to CTAs segment-major, so a task's predecessor was
 //                   started ~n_clips / gridDim tasks earlier; its last pair publishes the state and a flag, the
@@ -15,8 +15,13 @@
 //                   which yields the segment's aggregate (the recurrence is linear), then, after a look-back over the
 //                   aggregates of the segments before it (all produced concurrently), again from the true state with
 //                   output.  Twice the arithmetic, on a GPU that would otherwise idle; one launch.
-// [SPEC] "non-finite X^ -> 0" is applied per frame: one integer max over the lane's magnitudes per pair decides
-// whether the slow, per-value path is needed.
+// [SPEC] "non-finite X^ -> 0" is applied per frame: one integer max over the lane's powers per pair decides whether
+// the slow, per-value path is needed.  In the aggregate pass the sign bit of a state value records that a non-finite
+// frame wiped that bin inside the segment (X^ itself is never negative), so the look-back drops what came in from
+// earlier segments.
+// A warp-specialised form (10 producer warps leaving |2X|^2 in their planes, 2 consumer warps doing the recurrence and
+// the epilogue in pair order, state in registers) was built and measured at 218-244 M frames/s against 470 M for this
+// one: a single ordered warp only ever gets its fair share of a scheduler's issue slots.
 #pragma once
 #include "kernel_w32x2p.cuh"
 
@@ -85,7 +90,7 @@ __device__ __forceinline__ int xs_bin(int i, int lane, int half) {
 }
 
 // LATE: the next pair's loads are issued after the turn has been passed on (in the epilogue) instead of inside the untangle
-template <int OUT, int NW, int HOPJ, bool LATE, int K, bool NOSYNC = false>
+template <int OUT, int NW, int HOPJ, bool LATE, int K>
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
@@ -299,7 +304,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     }
     static_for<0, K>([&](auto cc) {
       constexpr int c = decltype(cc)::value, i0 = c * (16 / K), i1 = i0 + 16 / K;
-      if constexpr (!NOSYNC) while (!mbar_try_wait(s_bar + c * NW + warp, turn)) {}
+      while (!mbar_try_wait(s_bar + c * NW + warp, turn)) {}
       if (p == 0) {
         // first pair of a work item: the state the segment starts from
         const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;

@@ -5,14 +5,14 @@
 
 namespace sg {
 
-template <int OUT, int HOPJ, int NW, bool LATE, int K, bool NOSYNC = false>
+template <int OUT, int HOPJ, int NW, bool LATE, int K>
 static int launch_xs(const FrameGeom& g, const XsGeom& x, const W32Plan& p, const Epilogue& ep, void* out, int grid,
                      int device, cudaStream_t st) {
   using T = typename OutElem<OUT>::type;
   constexpr int smem = XsShape<NW>::kSmemBytes;
-  const cudaError_t rc = ensure_dynamic_smem<stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K, NOSYNC>>(smem, device);
+  const cudaError_t rc = ensure_dynamic_smem<stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K>>(smem, device);
   if (rc != cudaSuccess) return (int)rc;
-  stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K, NOSYNC><<<grid, NW * 32, smem, st>>>(g, x, p, ep, (T*)out);
+  stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K><<<grid, NW * 32, smem, st>>>(g, x, p, ep, (T*)out);
   return (int)cudaGetLastError();
 }
 
@@ -20,19 +20,12 @@ int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Pl
                   int grid, int device, cudaStream_t st) {
   return dispatch_out(out_kind, [&](auto tag) {
     constexpr int OUT = decltype(tag)::value;
-    static const int variant = [] { const char* v = getenv("SG_XS_VARIANT"); return v ? atoi(v) : 0; }();   // A/B runs
-    if (g.hop == 256) return launch_xs<OUT, 4, 8, true, 4>(g, x, p, ep, out, grid, device, st);
-    if constexpr (OUT == kOutU8) {
-      if (variant == 1) return launch_xs<OUT, 8, 8, true, 1>(g, x, p, ep, out, grid, device, st);
-      if (variant == 2) return launch_xs<OUT, 8, 8, true, 2>(g, x, p, ep, out, grid, device, st);
-      if (variant == 3) return launch_xs<OUT, 8, 12, true, 4>(g, x, p, ep, out, grid, device, st);
-      if (variant == 4) return launch_xs<OUT, 8, 12, true, 2>(g, x, p, ep, out, grid, device, st);
-      if (variant == 5) return launch_xs<OUT, 8, 8, false, 4>(g, x, p, ep, out, grid, device, st);
-      if (variant == 6) return launch_xs<OUT, 8, 8, true, 1, true>(g, x, p, ep, out, grid, device, st);
-      if (variant == 7) return launch_xs<OUT, 8, 12, true, 1, true>(g, x, p, ep, out, grid, device, st);
-      if (variant == 8) return launch_xs<OUT, 8, 12, true, 1>(g, x, p, ep, out, grid, device, st);
-    }
-    return launch_xs<OUT, 8, 8, true, 4>(g, x, p, ep, out, grid, device, st);
+    // 8 warps x 255 registers, the next pair's loads issued after the turn has been passed on, one turn chain
+    // (measured, 512 clips x 858 frames, u8: 470 M frames/s; 12 warps with the same chain 251 M -- 26 spilled words
+    //  and three warps per scheduler waiting on one ring; four chains over slot groups 433 M; loads inside the
+    //  untangle 409 M; without waiting at all, wrong results, 518 M: the ordering itself costs 9 %)
+    if (g.hop == 256) return launch_xs<OUT, 4, 8, true, 1>(g, x, p, ep, out, grid, device, st);
+    return launch_xs<OUT, 8, 8, true, 1>(g, x, p, ep, out, grid, device, st);
   });
 }
 
