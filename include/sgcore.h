@@ -128,7 +128,9 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
  * oracle) and for A/B timing:  0 = automatic;  1 = generic shared-memory kernel for every shape;
  * 2 = n_fft 2048 on the one-frame-per-warp kernel;  3 = n_fft 2048 on the register family (wreg);
  * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;
- * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM.
+ * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM;
+ * 7 = smoothingTimeConstant > 0 at n_fft 2048 / hop 512 or 256 on the fused one-pass kernel for ANY clip count
+ *     (automatic selection takes it from ~2/3 of the SM count in clips, and the two-kernel path below that).
  * 3 also selects the register family for n_fft 256 / 512 / 1024 (which have dedicated kernels by default). */
 int sg_engine_set_kernel_variant(sg_engine* e, int variant);
 
