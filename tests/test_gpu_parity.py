@@ -561,7 +561,14 @@ def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, ho
     sel = np.unique(np.r_[0, min(1, n_clips - 1), n_clips // 2, n_clips - 1])
     cfg = O.Config(n_fft=2048, hop=hop, smoothing=0.8, align=align, output=O.OUT_F32_MAG)
     ref_mag = O.spectrogram(x[sel], cfg)
-XX
+    for out in ("mag", "db", "u8", "rgba"):
+        opts = sg.Options(fftSize=2048, hop=hop, output=out, smoothingTimeConstant=0.8, align=ALIGN[align])
+        engine.set_kernel_variant(7)      # the fused kernel at any clip count (auto: only from ~2/3 of the SMs in clips)
+        try:
+            got = engine.spectrogram(x, opts)
+        finally:
+            engine.set_kernel_variant(0)
+        assert engine.last_kernel == "warp32x32x2s"
         if out == "mag":
             assert_mag_close(got[sel], ref_mag)
         elif out == "db":
