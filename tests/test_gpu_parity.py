@@ -582,25 +582,38 @@ def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, ho
 
 def test_fused_smoothing_chained_segments_are_the_sequential_arithmetic(engine):
     """Chain mode hands the float state from segment to segment: cutting a clip into segments must not change a bit.
-    The same clips as a small batch (few mode, look-back over float aggregates) agree to rounding."""
+    The same clips as a small batch (look-back over float aggregates, or the two-kernel path) agree to rounding.
+    Device-resident batches: the host entry cuts 200 clips into chunks of ~38, below the fused kernel's threshold."""
+    import torch
     rng = np.random.default_rng(5)
     clip_len = 2048 + 400 * 512
-    x = (0.2 * rng.standard_normal((200, clip_len))).astype(np.float32)
+    x = torch.from_numpy((0.2 * rng.standard_normal((200, clip_len))).astype(np.float32)).cuda()
     opts = sg.Options(fftSize=2048, hop=512, output="mag", smoothingTimeConstant=0.75)
-    a = engine.spectrogram(x, opts)                    # 200 clips: chained segments
+    frames = engine.num_frames(opts, clip_len)
+
+    def run(n):
+        out = torch.empty((n, frames, 1024), dtype=torch.float32, device="cuda")
+        engine.spectrogram_device(x.data_ptr(), n, clip_len, clip_len, opts, out.data_ptr())
+        engine.synchronize()
+        return out.cpu().numpy()
+
+    a = run(200)                                       # chained segments
     assert engine.last_kernel == "warp32x32x2s"
-    b = engine.spectrogram(x[:150], opts)              # another split of the same clips
+    b = run(150)                                       # another split of the same clips into tasks
+    assert engine.last_kernel == "warp32x32x2s"
     assert np.array_equal(a[:150], b)
     engine.set_kernel_variant(7)
     try:
-        c = engine.spectrogram(x[:2], opts)            # few mode: look-back over float aggregates
+        c = run(2)                                     # look-back over float aggregates
         assert engine.last_kernel == "warp32x32x2s"
     finally:
         engine.set_kernel_variant(0)
     assert np.max(np.abs(c - a[:2]) / (np.abs(a[:2]) + 1e-30)) < 5e-6
-    d = engine.spectrogram(x[:2], opts)                # auto: two clips take the two-kernel path
+    d = run(2)                                         # auto: two clips take the two-kernel path
     assert engine.last_kernel != "warp32x32x2s"
     assert np.max(np.abs(d - a[:2]) / (np.abs(a[:2]) + 1e-30)) < 5e-6
+    ref = O.spectrogram(x[:1].cpu().numpy(), O.Config(n_fft=2048, hop=512, smoothing=0.75, output=O.OUT_F32_MAG))
+    assert_mag_close(a[:1], ref)
 
 
 def test_fused_smoothing_non_finite_frames_reset_the_state(engine):
