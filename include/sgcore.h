@@ -117,9 +117,20 @@ int sg_stft_elem_bytes(const sg_stft_config* cfg);
 int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len,
                   const sg_stft_config* cfg, void* out);
 
+/* Clips sharded over several engines, one per GPU: engine s takes the contiguous block of clips
+ * [n_clips*s/G, n_clips*(s+1)/G); one host thread per engine inside the library runs sg_stft_batch's copy/compute
+ * pipeline on its block and writes its results into its own slice of `out` -- that host copy is the gather, the
+ * shards exchange nothing (no collective).  The result is bit-identical to sg_stft_batch on one engine.
+ * Replaces, for a batch of offline clips, G independent copies of the reference's frame loop
+ * (UI/spectrogram.js:153-161 + 3D/visualizer.js:399-416).  An engine may appear only once in the list. */
+int sg_stft_batch_multi(sg_engine* const* engines, int n_engines, const float* pcm, int64_t n_clips,
+                        int64_t clip_len, const sg_stft_config* cfg, void* out);
+
 /* Same, on DEVICE-resident buffers, asynchronous on `cuda_stream` (a cudaStream_t / CUstream
  * handle; NULL = the engine's own stream).  clip_stride = samples between clip starts
- * (>= clip_len).  pcm_dev and out_dev must be 16-byte aligned.  Does not synchronise. */
+ * (>= clip_len).  pcm_dev and out_dev must be 16-byte aligned.  Does not synchronise.
+ * Calls with smoothing > 0 (or a custom colormap) share the engine's scratch buffers: the engine orders such a call
+ * after the previous one with an event, whatever streams the two were given, so they serialise on the device. */
 int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, int64_t clip_len,
                          int64_t clip_stride, const sg_stft_config* cfg, void* out_dev,
                          void* cuda_stream);
@@ -191,6 +202,8 @@ int sg_stream_reset(sg_stream* s); /* zero history and smoothing state */
  * colour LUT (only when cfg.output == SG_OUT_U8).  Synchronous: returns when both are filled. */
 int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, uint32_t* out_rgba);
 int64_t sg_stream_frames_emitted(const sg_stream* s); /* per channel */
+/* geometry of a stream object (any pointer may be NULL): what a binding needs to check the caller's array lengths */
+int sg_stream_info(const sg_stream* s, int* channels, int* hop, int* bins, int* output, int* max_chunk);
 
 /* ------------------------------------------------------------------ PCM ingestion ---------- */
 /* The step in front of the path: the reference hands an encoded file to the browser,
@@ -257,6 +270,7 @@ int sg_ring_reset(sg_ring* r); /* texture cleared to 0, yoffset 0 (initByteBuffe
 /* texSubImage2D of n_rows consecutive frames (host [n_rows][bins] u8), wrapping at `rows` */
 int sg_ring_append(sg_ring* r, const uint8_t* frames, int n_rows);
 int sg_ring_yoffset(const sg_ring* r);
+int sg_ring_info(const sg_ring* r, int* bins, int* rows);   /* either pointer may be NULL */
 /* the whole texture, host [rows][bins], in texture row order */
 int sg_ring_read(sg_ring* r, uint8_t* dst);
 /* Headless restatement of the sonogram view as an RGBA8 image, host [height][width]:

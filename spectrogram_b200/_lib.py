@@ -74,6 +74,8 @@ SIGNATURES = {
     "sg_stft_num_frames": (C.c_int64, [C.POINTER(StftConfig), C.c_int64]),
     "sg_stft_elem_bytes": (C.c_int, [C.POINTER(StftConfig)]),
     "sg_stft_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(StftConfig), C.c_void_p]),
+    "sg_stft_batch_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(StftConfig),
+                                      C.c_void_p]),
     "sg_stft_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                        C.POINTER(StftConfig), C.c_void_p, C.c_void_p]),
     "sg_colormap_reference": (C.c_int, [C.c_void_p]),
@@ -98,6 +100,7 @@ SIGNATURES = {
     "sg_stream_reset": (C.c_int, [C.c_void_p]),
     "sg_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sg_stream_frames_emitted": (C.c_int64, [C.c_void_p]),
+    "sg_stream_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
     "sg_pcm_sample_bytes": (C.c_int, [C.c_int]),
     "sg_pcm_num_planes": (C.c_int, [C.POINTER(PcmInfo), C.c_int]),
     "sg_wav_parse": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(PcmInfo)]),
@@ -111,6 +114,7 @@ SIGNATURES = {
     "sg_ring_reset": (C.c_int, [C.c_void_p]),
     "sg_ring_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "sg_ring_yoffset": (C.c_int, [C.c_void_p]),
+    "sg_ring_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sg_ring_read": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sg_ring_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -267,35 +267,30 @@ def shard_bounds(n_units: int, n_shards: int) -> list[tuple[int, int]]:
 
 def spectrogram(pcm, devices=None, **kw) -> np.ndarray:
     """Batched frame path.  ``devices``: None/int -> one GPU; list -> clips sharded in contiguous
-    blocks, one host thread + engine per GPU, results gathered by host copy into one array (no
-    collective; shards are independent)."""
+    blocks over one engine per GPU by ``sg_stft_batch_multi`` (a host thread per engine inside the
+    library), results gathered by host copy into one array (no collective; shards are independent)."""
     opts = kw.pop("opts", None) or Options(**kw)
     if devices is None or isinstance(devices, int):
         return default_engine(devices or 0).spectrogram(pcm, opts)
     x = np.ascontiguousarray(np.atleast_2d(np.asarray(pcm, dtype=np.float32)))
     devs = list(devices)
-    eng0 = default_engine(devs[0])
+    if len(set(devs)) != len(devs):
+        raise TypeError("a device may be listed only once")
+    return spectrogram_multi([default_engine(d) for d in devs], x, opts)
+
+
+def spectrogram_multi(engines, pcm, opts: Options) -> np.ndarray:
+    """``sg_stft_batch_multi`` on explicit engines (normally one per GPU; several engines on one GPU also work)."""
+    x = np.ascontiguousarray(np.atleast_2d(np.asarray(pcm, dtype=np.float32)))
+    engs = list(engines)
     cfg, _keep = opts.to_c()
-    frames = eng0.num_frames(opts, x.shape[1])
+    frames = engs[0].num_frames(opts, x.shape[1])
     dt, shape = out_dtype_shape(cfg.output, x.shape[0], frames, cfg.n_fft // 2)
     out = np.empty(shape, dtype=dt)
-    errs: list[BaseException] = []
-
-    def work(dev, lo, hi):
-        try:
-            if hi > lo:
-                default_engine(dev).spectrogram(x[lo:hi], opts, out=out[lo:hi])
-        except BaseException as e:  # surfaced below
-            errs.append(e)
-
-    threads = [threading.Thread(target=work, args=(d, lo, hi))
-               for d, (lo, hi) in zip(devs, shard_bounds(x.shape[0], len(devs)))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errs:
-        raise errs[0]
+    # sg_stft_batch_multi: contiguous clip blocks, one host thread per engine inside the library, disjoint output slices
+    handles = (C.c_void_p * len(engs))(*[e.handle for e in engs])
+    L.check(L.load().sg_stft_batch_multi(handles, len(engs), x.ctypes.data, x.shape[0], x.shape[1], C.byref(cfg),
+                                         out.ctypes.data))
     return out
 
 

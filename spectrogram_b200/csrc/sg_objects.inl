@@ -59,6 +59,7 @@ struct sg_analyser {
     Plan* pl;
     SG_TRY(e->get_plan(c, &pl));
     sg::FrameGeom g{(const float*)d_block.p, n, n, 1, 1, 0, n, n};
+    SG_TRY(e->scratch_acquire(e->stream));
     SG_TRY(launch_frames(e, *pl, g, c, SG_OUT_F32_MAG, e->lut_ref, d_mag.p, e->stream));
     const sg::Epilogue ep = make_epilogue(c, 2.0 * n, e->lut_ref);
     SG_TRY(launch_smooth(e, SG_OUT_F32_MAG, (const float*)d_mag.p, (float*)d_mag.p + bins, (float*)d_state.p, 1, 1, bins, tau, ep,
@@ -319,6 +320,15 @@ int sg_stream_destroy(sg_stream* s) {
 }
 
 int64_t sg_stream_frames_emitted(const sg_stream* s) { return s ? s->frames_emitted : 0; }
+int sg_stream_info(const sg_stream* s, int* channels, int* hop, int* bins, int* output, int* max_chunk) {
+  if (!s) return fail(SG_ERR_INVALID_ARG, "stream is null");
+  if (channels) *channels = s->channels;
+  if (hop) *hop = s->cfg.hop;
+  if (bins) *bins = s->cfg.n_fft / 2;
+  if (output) *output = s->cfg.output;
+  if (max_chunk) *max_chunk = s->max_chunk;
+  return SG_OK;
+}
 
 int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, uint32_t* out_rgba) {
   if (!s) return fail(SG_ERR_INVALID_ARG, "stream is null");
@@ -359,6 +369,7 @@ int sg_stream_push(sg_stream* s, const float* chunk, int chunk_len, void* out, u
   // frame t ends at history + (t+1)*hop: with the row shifted by hop it is the "valid" geometry
   Plan* pl;
   SG_TRY(e->get_plan(c, &pl));
+  if (c.smoothing != 0.f) SG_TRY(e->scratch_acquire(st));   // an asynchronous sg_stft_batch_device call may still hold the scratch
   const uint32_t* lut;
   SG_TRY(e->lut_for(c, st, &lut));
   SG_TRY(run_range(e, *pl, c, hist + c.hop, ch, (long long)n + chunk_len - c.hop, s->pitch, 0, frames, frames,
@@ -432,6 +443,12 @@ int sg_ring_destroy(sg_ring* r) {
 }
 
 int sg_ring_yoffset(const sg_ring* r) { return r ? r->yoffset : SG_ERR_INVALID_ARG; }
+int sg_ring_info(const sg_ring* r, int* bins, int* rows) {
+  if (!r) return fail(SG_ERR_INVALID_ARG, "ring is null");
+  if (bins) *bins = r->bins;
+  if (rows) *rows = r->rows;
+  return SG_OK;
+}
 
 int sg_ring_append(sg_ring* r, const uint8_t* frames, int n_rows) {
   if (!r) return fail(SG_ERR_INVALID_ARG, "ring is null");

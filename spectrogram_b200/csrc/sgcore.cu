@@ -15,6 +15,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernel_misc.cuh"
@@ -347,6 +348,21 @@ struct sg_engine {
   int kernel_variant = 0;            // 0 auto, 1 force generic smem kernel
   const char* last_kernel = "none";
   std::mutex mu;
+  // The scratch buffers above (smoothing state, magnitude tiles, carry vectors, the custom colour table) are shared by
+  // every call on this engine, whatever stream the caller passes.  A call that uses them first makes its stream wait
+  // for the previous user's last kernel and records its own end on this event afterwards.
+  cudaEvent_t ev_scratch = nullptr;
+  cudaEvent_t ev_ring_in[4] = {}, ev_ring_k[4] = {}, ev_pin_in[2] = {}, ev_pin_out[2] = {};   // sg_stft_batch's pipeline
+  bool scratch_busy = false;
+  int scratch_acquire(cudaStream_t st) {
+    if (scratch_busy) SG_CUDA(cudaStreamWaitEvent(st, ev_scratch, 0));
+    return SG_OK;
+  }
+  int scratch_release(cudaStream_t st) {
+    SG_CUDA(cudaEventRecord(ev_scratch, st));
+    scratch_busy = true;
+    return SG_OK;
+  }
 
   int get_plan(const sg_stft_config& cfg, Plan** out) {
     PlanKey key{cfg.n_fft, cfg.window,
@@ -363,7 +379,7 @@ struct sg_engine {
   }
 
   int lut_for(const sg_stft_config& cfg, cudaStream_t st, const uint32_t** out) {
-    if (!cfg.colormap) { *out = lut_ref; return SG_OK; }
+    if (!cfg.colormap || cfg.output != SG_OUT_RGBA8) { *out = lut_ref; return SG_OK; }
     SG_TRY(lut_user.reserve(256 * sizeof(uint32_t)));
     SG_CUDA(cudaMemcpyAsync(lut_user.p, cfg.colormap, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     *out = (const uint32_t*)lut_user.p;
@@ -691,18 +707,35 @@ int sg_engine_create(int device, sg_engine** out) {
   SG_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   SG_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail(SG_ERR_NO_DEVICE, "device is not Blackwell (sm_100a kernels only)");
+  if (prop.major != 10)     // the library holds sm_100a code only: sm_90 and sm_120 parts have no kernel image
+    return fail(SG_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
   sg_engine* e = new sg_engine();
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
-  SG_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  SG_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
-  SG_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
-  uint32_t lut[256];
-  reference_lut(lut);
-  SG_CUDA(cudaMalloc((void**)&e->lut_ref, sizeof(lut)));
-  SG_CUDA(cudaMemcpy(e->lut_ref, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  const int rc = [&]() -> int {
+    SG_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    SG_CUDA(cudaEventCreateWithFlags(&e->ev_scratch, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) {
+      SG_CUDA(cudaEventCreateWithFlags(&e->ev_ring_in[i], cudaEventDisableTiming));
+      SG_CUDA(cudaEventCreateWithFlags(&e->ev_ring_k[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) {
+      SG_CUDA(cudaEventCreateWithFlags(&e->ev_pin_in[i], cudaEventDisableTiming));
+      SG_CUDA(cudaEventCreateWithFlags(&e->ev_pin_out[i], cudaEventDisableTiming));
+    }
+    uint32_t lut[256];
+    reference_lut(lut);
+    SG_CUDA(cudaMalloc((void**)&e->lut_ref, sizeof(lut)));
+    SG_CUDA(cudaMemcpy(e->lut_ref, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    return SG_OK;
+  }();
+  if (rc != SG_OK) {          // nothing half-built is left behind
+    const std::string why = g_err;
+    sg_engine_destroy(e);
+    return fail(rc, why);
+  }
   *out = e;
   return SG_OK;
 }
@@ -716,7 +749,12 @@ int sg_engine_destroy(sg_engine* e) {
   e->lut_user.release(); e->scratch_mag.release(); e->scratch_state.release(); e->scratch_carry.release(); e->xs_carry.release(); e->xs_flags.release(); e->xs_state.release(); e->d_in.release(); e->d_out.release();
   e->d_raw[0].release(); e->d_raw[1].release();
   for (int i = 0; i < 2; ++i) { e->pin_in[i].release(); e->pin_out[i].release(); }
-  cudaStreamDestroy(e->stream); cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_d2h);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  if (e->ev_scratch) cudaEventDestroy(e->ev_scratch);
+  for (int i = 0; i < 4; ++i) { if (e->ev_ring_in[i]) cudaEventDestroy(e->ev_ring_in[i]); if (e->ev_ring_k[i]) cudaEventDestroy(e->ev_ring_k[i]); }
+  for (int i = 0; i < 2; ++i) { if (e->ev_pin_in[i]) cudaEventDestroy(e->ev_pin_in[i]); if (e->ev_pin_out[i]) cudaEventDestroy(e->ev_pin_out[i]); }
   delete e;
   return SG_OK;
 }
@@ -766,10 +804,14 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
   Plan* pl;
   SG_TRY(e->get_plan(*cfg, &pl));
-  const uint32_t* lut;
-  SG_TRY(e->lut_for(*cfg, st, &lut));
   const long long frames = frames_for(*cfg, clip_len);
   if (frames == 0) return SG_OK;
+  // the engine's scratch (smoothing state / magnitude tiles / carries, the custom colour table) is shared by all
+  // streams: order this call after the previous user, whatever stream that was on
+  const bool shared = cfg->smoothing != 0.f || (cfg->colormap && cfg->output == SG_OUT_RGBA8);
+  if (shared) SG_TRY(e->scratch_acquire(st));
+  const uint32_t* lut;
+  SG_TRY(e->lut_for(*cfg, st, &lut));
   float* state = nullptr;
   if (cfg->smoothing != 0.f) {
     const size_t sb = (size_t)n_clips * (cfg->n_fft / 2) * sizeof(float);
@@ -777,7 +819,9 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
     SG_CUDA(cudaMemsetAsync(e->scratch_state.p, 0, sb, st));
     state = (float*)e->scratch_state.p;
   }
-  return run_range(e, *pl, *cfg, pcm_dev, n_clips, clip_len, clip_stride, 0, frames, frames, out_dev, state, lut, st);
+  SG_TRY(run_range(e, *pl, *cfg, pcm_dev, n_clips, clip_len, clip_stride, 0, frames, frames, out_dev, state, lut, st));
+  if (shared) SG_TRY(e->scratch_release(st));
+  return SG_OK;
 }
 
 // Host buffers.  Work is cut into chunks (groups of whole clips, or frame ranges of one long clip);
@@ -804,6 +848,7 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
   SG_CUDA(cudaSetDevice(e->device));
   Plan* pl;
   SG_TRY(e->get_plan(*cfg, &pl));
+  SG_TRY(e->scratch_acquire(e->stream));     // an earlier sg_stft_batch_device call on another stream may still use it
   const uint32_t* lut;
   SG_TRY(e->lut_for(*cfg, e->stream, &lut));
   const long long frames = frames_for(*cfg, clip_len);
@@ -827,21 +872,28 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
     state = (float*)e->scratch_state.p;
   }
   const bool in_pinned = is_pinned(pcm), out_pinned = is_pinned(out);
-  const size_t kChunk = 32u << 20;  // target bytes per chunk (input side)
+  // target bytes per chunk, whichever side (input or output) is larger: at small hops a frame's output dwarfs its hop.
+  // Raw 16-bit PCM moves half the input bytes per sample: larger chunks keep its copies as long as the float path's.
+  const size_t kChunk = (raw ? 64u : 32u) << 20;
   struct Chunk { long long c0, nc, t0, nt; };
   std::vector<Chunk> chunks;
   const size_t clip_bytes = (size_t)clip_len * unit;
-  if (clip_bytes <= kChunk) {
-    const long long per = std::max<long long>(1, (long long)(kChunk / std::max<size_t>(clip_bytes, 1)));
+  const size_t clip_out_bytes = (size_t)planes * frames * bins * eb;
+  if (std::max(clip_bytes, clip_out_bytes) <= kChunk) {
+    const long long per = std::max<long long>(1, (long long)(kChunk / std::max<size_t>(std::max(clip_bytes, clip_out_bytes), 1)));
     for (long long c = 0; c < n_clips; c += per) chunks.push_back({c, std::min(per, n_clips - c), 0, frames});
   } else {
-    const long long per = std::max<long long>(1, (long long)(kChunk / ((size_t)cfg->hop * unit)));
+    const long long per = std::max<long long>(1, (long long)(kChunk / std::max((size_t)cfg->hop * unit, (size_t)planes * bins * eb)));
     for (long long c = 0; c < n_clips; ++c)
       for (long long t = 0; t < frames; t += per) chunks.push_back({c, 1, t, std::min(per, frames - t)});
   }
   const long long start_base = cfg->align == SG_ALIGN_VALID ? 0 : (long long)cfg->hop - cfg->n_fft;
-  std::vector<cudaEvent_t> ev_in(chunks.size()), ev_k(chunks.size());
-  cudaEvent_t ev_pin_in[2] = {nullptr, nullptr}, ev_pin_out[2] = {nullptr, nullptr};
+  // events of the pipeline: the engine's own (created once), chunk i uses slot i & 3
+  cudaEvent_t* const ev_in = e->ev_ring_in;
+  cudaEvent_t* const ev_k = e->ev_ring_k;
+  cudaEvent_t* const ev_pin_in = e->ev_pin_in;
+  cudaEvent_t* const ev_pin_out = e->ev_pin_out;
+  bool pin_in_used[2] = {false, false};
   // a chunk's output is `rows` runs of `width` bytes, `pitch` apart (one run, or one per plane for a frame range)
   struct Pending { char* dst; size_t width, pitch; int rows; bool live; } pend[2] = {{nullptr, 0, 0, 0, false}, {nullptr, 0, 0, 0, false}};
   int rc = SG_OK;
@@ -853,20 +905,12 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
     pend[slot].live = false;
     return SG_OK;
   };
-  for (auto& ev : ev_in) ev = nullptr;
-  for (auto& ev : ev_k) ev = nullptr;
   auto body = [&]() -> int {
-    for (int i = 0; i < 2; ++i) {
-      SG_CUDA(cudaEventCreateWithFlags(&ev_pin_in[i], cudaEventDisableTiming));
-      SG_CUDA(cudaEventCreateWithFlags(&ev_pin_out[i], cudaEventDisableTiming));
-    }
     long long uploaded_to = 0;  // per-clip sample watermark for frame-range chunks
     long long uploaded_clip = -1;
     for (size_t i = 0; i < chunks.size(); ++i) {
       const Chunk& ch = chunks[i];
       const int slot = (int)(i & 1);
-      SG_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-      SG_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
       // ---- host -> device
       long long s_lo, s_hi;  // sample range of each clip in this chunk
       if (ch.nt == frames) { s_lo = 0; s_hi = clip_len; }
@@ -883,24 +927,28 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
         size_t dpitch = (size_t)stride * sizeof(float);
         if (raw) {                                            // raw PCM: dense rows in this slot's byte buffer
           SG_TRY(e->d_raw[slot].reserve(row * ch.nc + 32));
-          if (i >= 2) SG_CUDA(cudaStreamWaitEvent(e->s_h2d, ev_k[i - 2], 0));   // its last reader has finished
+          if (i >= 2) SG_CUDA(cudaStreamWaitEvent(e->s_h2d, ev_k[(i - 2) & 3], 0));   // its last reader has finished
           dst = (char*)e->d_raw[slot].p;
           dpitch = row;
         }
         if (!in_pinned) {
           SG_TRY(e->pin_in[slot].reserve(row * ch.nc));
-          SG_CUDA(cudaEventSynchronize(ev_pin_in[slot]));   // previous use of this bounce has been copied
+          if (pin_in_used[slot]) SG_CUDA(cudaEventSynchronize(ev_pin_in[slot]));   // previous use of this bounce has been copied
           for (long long c = 0; c < ch.nc; ++c)
             std::memcpy((char*)e->pin_in[slot].p + c * row, src + c * clip_bytes, row);
-          SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, e->pin_in[slot].p, row, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
+          // (one clip per chunk: a plain copy -- a 2-D copy's pitch is limited to 2^31 - 1 bytes)
+          if (ch.nc == 1) SG_CUDA(cudaMemcpyAsync(dst, e->pin_in[slot].p, row, cudaMemcpyHostToDevice, e->s_h2d));
+          else SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, e->pin_in[slot].p, row, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
           SG_CUDA(cudaEventRecord(ev_pin_in[slot], e->s_h2d));
+          pin_in_used[slot] = true;
         } else {
-          SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, clip_bytes, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
+          if (ch.nc == 1) SG_CUDA(cudaMemcpyAsync(dst, src, row, cudaMemcpyHostToDevice, e->s_h2d));
+          else SG_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, clip_bytes, row, ch.nc, cudaMemcpyHostToDevice, e->s_h2d));
         }
       }
-      SG_CUDA(cudaEventRecord(ev_in[i], e->s_h2d));
+      SG_CUDA(cudaEventRecord(ev_in[i & 3], e->s_h2d));
       // ---- kernels
-      SG_CUDA(cudaStreamWaitEvent(e->stream, ev_in[i], 0));
+      SG_CUDA(cudaStreamWaitEvent(e->stream, ev_in[i & 3], 0));
       if (raw && row > 0) {
         PcmGeom pg;
         pg.src = (const unsigned char*)e->d_raw[slot].p;
@@ -919,9 +967,9 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
       SG_TRY(run_range(e, *pl, *cfg, d_in + ch.c0 * planes * stride, ch.nc * planes, clip_len, stride, ch.t0, ch.nt, frames,
                        d_out + (size_t)ch.c0 * planes * frames * bins * eb, state ? state + ch.c0 * planes * bins : nullptr,
                        lut, e->stream));
-      SG_CUDA(cudaEventRecord(ev_k[i], e->stream));
+      SG_CUDA(cudaEventRecord(ev_k[i & 3], e->stream));
       // ---- device -> host
-      SG_CUDA(cudaStreamWaitEvent(e->s_d2h, ev_k[i], 0));
+      SG_CUDA(cudaStreamWaitEvent(e->s_d2h, ev_k[i & 3], 0));
       const size_t off = ((size_t)ch.c0 * planes * frames + ch.t0) * bins * eb;
       const bool whole = ch.nt == frames;
       const size_t width = (whole ? (size_t)ch.nc * planes * frames : (size_t)ch.nt) * bins * eb;
@@ -947,9 +995,6 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
   };
   rc = body();
   if (rc != SG_OK) cudaDeviceSynchronize();
-  for (auto ev : ev_in) if (ev) cudaEventDestroy(ev);
-  for (auto ev : ev_k) if (ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) { if (ev_pin_in[i]) cudaEventDestroy(ev_pin_in[i]); if (ev_pin_out[i]) cudaEventDestroy(ev_pin_out[i]); }
   return rc;
 }
 }  // namespace
@@ -958,6 +1003,42 @@ extern "C" {
 int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,
                   void* out) {
   return stft_batch_impl(e, pcm, n_clips, clip_len, cfg, out, nullptr);
+}
+
+// Clips sharded over several engines (one per GPU): engine s takes the contiguous block
+// [n_clips*s/G, n_clips*(s+1)/G), one host thread per engine runs the three-stream pipeline of sg_stft_batch on its
+// block, and every block's results land in its own slice of the caller's `out` -- that host copy is the gather; the
+// shards exchange nothing.  Bit-identical to one engine processing all clips.
+int sg_stft_batch_multi(sg_engine* const* engines, int n_engines, const float* pcm, int64_t n_clips, int64_t clip_len,
+                        const sg_stft_config* cfg, void* out) {
+  if (!engines || n_engines < 1) return fail(SG_ERR_INVALID_ARG, "need at least one engine");
+  for (int s = 0; s < n_engines; ++s) {
+    if (!engines[s]) return fail(SG_ERR_INVALID_ARG, "null engine");
+    for (int t = 0; t < s; ++t)
+      if (engines[t] == engines[s]) return fail(SG_ERR_INVALID_ARG, "the same engine listed twice");
+  }
+  SG_TRY(validate_cfg(cfg));
+  if (n_clips < 0 || clip_len < 0) return fail(SG_ERR_INVALID_ARG, "bad clip geometry");
+  if (n_clips == 0) return SG_OK;
+  if (!pcm || !out) return fail(SG_ERR_INVALID_ARG, "null host buffer");
+  if (n_engines == 1) return stft_batch_impl(engines[0], pcm, n_clips, clip_len, cfg, out, nullptr);
+  const size_t out_clip = (size_t)frames_for(*cfg, clip_len) * (size_t)(cfg->n_fft / 2) * elem_bytes(cfg->output);
+  std::vector<int> rc((size_t)n_engines, SG_OK);
+  std::vector<std::string> msg((size_t)n_engines);
+  std::vector<std::thread> workers;
+  for (int s = 0; s < n_engines; ++s) {
+    const int64_t lo = n_clips * s / n_engines, hi = n_clips * (s + 1) / n_engines;
+    if (hi <= lo) continue;
+    workers.emplace_back([=, &rc, &msg] {
+      rc[(size_t)s] = stft_batch_impl(engines[s], pcm + (size_t)lo * (size_t)clip_len, hi - lo, clip_len, cfg,
+                                      (char*)out + (size_t)lo * out_clip, nullptr);
+      if (rc[(size_t)s] != SG_OK) msg[(size_t)s] = g_err;      // g_err is thread local: carry it to the caller's thread
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int s = 0; s < n_engines; ++s)
+    if (rc[(size_t)s] != SG_OK) return fail(rc[(size_t)s], "engine " + std::to_string(s) + ": " + msg[(size_t)s]);
+  return SG_OK;
 }
 }  // extern "C"
 

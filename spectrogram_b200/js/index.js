@@ -48,12 +48,32 @@ function engineFor(device) {
   if (!engines.has(d)) engines.set(d, native.engineCreate(d));
   return engines.get(d);
 }
+// Engines live as long as the process uses the module; closeAll() releases their device and pinned memory.
+function closeAll() {
+  for (const e of engines.values()) native.engineDestroy(e);
+  engines.clear();
+}
+// Objects that were not close()d by hand release their native handle when they are collected.
+const reaper = typeof FinalizationRegistry === 'function'
+  ? new FinalizationRegistry(({ destroy, handle }) => { try { destroy(handle); } catch (err) { /* engine already gone */ } })
+  : null;
+function own(obj, destroy, handle) {
+  if (reaper) reaper.register(obj, { destroy, handle }, obj);
+}
+function disown(obj) {
+  if (reaper) reaper.unregister(obj);
+}
+function wholeNumber(v, what) {
+  if (!Number.isInteger(v) || v < 0) throw new TypeError(what + ' must be a whole number');
+  return v;
+}
 
 class AnalyserNode {
   constructor(options) {
     const o = options || {};
     this._engine = engineFor(o.device || 0);
     this._h = native.analyserCreate(this._engine);
+    own(this, native.analyserDestroy, this._h);
     if (o.fftSize !== undefined) this.fftSize = o.fftSize;
     if (o.minDecibels !== undefined) this.minDecibels = o.minDecibels;
     if (o.maxDecibels !== undefined) this.maxDecibels = o.maxDecibels;
@@ -96,7 +116,7 @@ class AnalyserNode {
     guard(native.getFloatTimeDomainData)(this._h, array);
   }
   close() {
-    if (this._h) native.analyserDestroy(this._h);
+    if (this._h) { disown(this); native.analyserDestroy(this._h); }
     this._h = null;
   }
 }
@@ -109,8 +129,9 @@ const OUT_CTOR = { u8: Uint8Array, byte: Uint8Array, db: Float32Array, float: Fl
  * reference appends to its texture, visualizer.js:399-416).
  * opts: { fftSize, hop, window, minDecibels, maxDecibels, smoothingTimeConstant, output, align,
  *         nClips, device | devices }
- * devices: [0, 1, ...] shards clips in contiguous blocks, one engine per GPU, results gathered by
- * host copy into one typed array (no collective; shards are independent).
+ * devices: [0, 1, ...] shards clips in contiguous blocks, one engine per GPU running concurrently (the library
+ * starts a host thread per engine), results gathered by host copy into one typed array (no collective; shards are
+ * independent).
  */
 function spectrogram(pcm, opts) {
   if (!(pcm instanceof Float32Array)) throw new TypeError('pcm must be a Float32Array');
@@ -124,13 +145,8 @@ function spectrogram(pcm, opts) {
   if (!Ctor) throw new TypeError('unknown output ' + o.output);
   const data = new Ctor(nClips * frames * bins);
   const devices = o.devices || [o.device || 0];
-  const G = devices.length;
-  for (let s = 0; s < G; s++) {
-    const lo = Math.floor((nClips * s) / G), hi = Math.floor((nClips * (s + 1)) / G);
-    if (hi <= lo) continue;
-    guard(native.stftBatch)(engineFor(devices[s]), pcm.subarray(lo * clipLen, hi * clipLen), hi - lo, clipLen, o,
-      data.subarray(lo * frames * bins, hi * frames * bins));
-  }
+  if (devices.length === 1) guard(native.stftBatch)(engineFor(devices[0]), pcm, nClips, clipLen, o, data);
+  else guard(native.stftBatchMulti)(devices.map(engineFor), pcm, nClips, clipLen, o, data);   // sg_stft_batch_multi: one host thread per GPU inside the library
   return { frames, bins, data };
 }
 
@@ -140,14 +156,15 @@ class StreamBank {
     this.nChannels = nChannels;
     this.maxChunk = maxChunk || this.opts.hop;
     this._h = guard(native.streamCreate)(engineFor(this.opts.device || 0), nChannels, this.opts, this.maxChunk);
+    own(this, native.streamDestroy, this._h);
   }
   // chunk: Float32Array [channel][chunkLen]; out: typed array [channel][chunkLen/hop][bins]
   push(chunk, out, outRgba) {
-    const chunkLen = chunk.length / this.nChannels;
+    const chunkLen = wholeNumber(chunk.length / this.nChannels, 'chunk.length / nChannels');
     guard(native.streamPush)(this._h, chunk, chunkLen, out, outRgba);
   }
   close() {
-    if (this._h) native.streamDestroy(this._h);
+    if (this._h) { disown(this); native.streamDestroy(this._h); }
     this._h = null;
   }
 }
@@ -160,10 +177,12 @@ class SonogramRing {
     this.bins = bins;
     this.rows = rows || 256;
     this._h = guard(native.ringCreate)(engineFor(device || 0), this.bins, this.rows);
+    own(this, native.ringDestroy, this._h);
   }
   // frames: Uint8Array holding one or more byte rows (what getByteFrequencyData filled)
   append(frames) {
-    guard(native.ringAppend)(this._h, frames, frames.length / this.bins);
+    if (!(frames instanceof Uint8Array)) throw new TypeError('frames must be a Uint8Array');
+    guard(native.ringAppend)(this._h, frames, wholeNumber(frames.length / this.bins, 'frames.length / bins'));
   }
   get yoffset() {
     return native.ringYoffset(this._h);
@@ -175,7 +194,7 @@ class SonogramRing {
     return img;
   }
   close() {
-    if (this._h) native.ringDestroy(this._h);
+    if (this._h) { disown(this); native.ringDestroy(this._h); }
     this._h = null;
   }
 }
@@ -233,7 +252,9 @@ function spectrogramPcm(samples, pcm, options) {
   const bins = o.fftSize / 2;
   const planes = o.mix ? 1 : (pcm.channels || 1);
   const n = o.clips * planes * frames * bins;
-  const data = o.output === 'u8' ? new Uint8Array(n) : (o.output === 'rgba' ? new Uint32Array(n) : new Float32Array(n));
+  const Ctor = OUT_CTOR[o.output];
+  if (!Ctor) throw new TypeError('unknown output ' + o.output);
+  const data = new Ctor(n);
   guard(native.stftPcm)(engineFor(o.device || 0), samples, pcm, o.clips, o.mix ? 1 : 0, o, data);
   return { frames, bins, planes, data };
 }
@@ -249,4 +270,5 @@ module.exports = {
   spectrogramPcm,
   colormapReference: () => native.colormapReference(),
   deviceCount: () => native.deviceCount(),
+  closeAll,
 };

@@ -240,6 +240,44 @@ static napi_value js_stft_batch(napi_env env, napi_callback_info info) {
   return undefined_of(env);
 }
 
+/* stftBatchMulti(engines: [engine, ...], pcm, nClips, clipLen, options, out): clips sharded over the engines in
+ * contiguous blocks inside the library (one host thread per engine), results gathered into `out` */
+static napi_value js_stft_batch_multi(napi_env env, napi_callback_info info) {
+  napi_value argv[MAX_ARGS], item;
+  sg_engine* engines[64];
+  void *e, *pcm, *out;
+  size_t pcm_len, out_len;
+  uint32_t n_eng = 0, i;
+  int64_t n_clips, clip_len, frames;
+  sg_stft_config cfg;
+  napi_typedarray_type want;
+  bool is_arr = false;
+  int rc;
+  if (get_args(env, info, argv) < 6) return type_error(env, "stftBatchMulti(engines, pcm, nClips, clipLen, options, out)");
+  if (napi_is_array(env, argv[0], &is_arr) != napi_ok || !is_arr || napi_get_array_length(env, argv[0], &n_eng) != napi_ok ||
+      n_eng < 1 || n_eng > 64)
+    return type_error(env, "engines must be an array of 1..64 engines");
+  for (i = 0; i < n_eng; ++i) {
+    if (napi_get_element(env, argv[0], i, &item) != napi_ok || !get_external(env, item, &e)) return type_error(env, "engine expected");
+    engines[i] = (sg_engine*)e;
+  }
+  if (!get_typed(env, argv[1], napi_float32_array, &pcm, &pcm_len)) return type_error(env, "pcm must be a Float32Array");
+  if (napi_get_value_int64(env, argv[2], &n_clips) != napi_ok || napi_get_value_int64(env, argv[3], &clip_len) != napi_ok)
+    return type_error(env, "nClips and clipLen must be numbers");
+  if (!parse_config(env, argv[4], &cfg)) return undefined_of(env);
+  if (n_clips < 0 || clip_len < 0 || (uint64_t)n_clips * (uint64_t)clip_len > pcm_len)
+    return type_error(env, "pcm is shorter than nClips * clipLen");
+  frames = sg_stft_num_frames(&cfg, clip_len);
+  if (frames < 0) return throw_status(env, SG_ERR_INDEX_SIZE);
+  want = cfg.output == SG_OUT_U8 ? napi_uint8_array : (cfg.output == SG_OUT_RGBA8 ? napi_uint32_array : napi_float32_array);
+  if (!get_typed(env, argv[5], want, &out, &out_len)) return type_error(env, "out has the wrong typed-array type for this output");
+  if ((uint64_t)out_len < (uint64_t)n_clips * (uint64_t)frames * (uint64_t)(cfg.n_fft / 2))
+    return type_error(env, "out is shorter than nClips * frames * bins");
+  rc = sg_stft_batch_multi(engines, (int)n_eng, (const float*)pcm, n_clips, clip_len, &cfg, out);
+  if (rc != SG_OK) return throw_status(env, rc);
+  return undefined_of(env);
+}
+
 static napi_value js_colormap_reference(napi_env env, napi_callback_info info) {
   napi_value ab, ta;
   void* data = NULL;
@@ -385,6 +423,22 @@ static napi_value js_stream_push(napi_env env, napi_callback_info info) {
     return type_error(env, "out must be a typed array");
   if (argc >= 5 && !is_undefined(env, argv[4]) && !get_typed(env, argv[4], napi_uint32_array, &rgba, &rgba_n))
     return type_error(env, "outRgba must be a Uint32Array");
+  {
+    /* the core reads channels * chunkLen samples and writes channels * (chunkLen / hop) * bins elements: check the
+     * caller's arrays against the stream's own geometry before handing raw pointers over */
+    int channels = 0, hop = 1, bins = 0, output = 0, max_chunk = 0;
+    napi_typedarray_type got = napi_uint8_array;
+    uint64_t need;
+    if (sg_stream_info((sg_stream*)s, &channels, &hop, &bins, &output, &max_chunk) != SG_OK) return type_error(env, "stream expected");
+    if (chunk_len < 0 || chunk_len > max_chunk || chunk_len % hop) return type_error(env, "chunkLen must be a multiple of hop, at most maxChunk");
+    if ((uint64_t)chunk_n < (uint64_t)channels * (uint64_t)chunk_len) return type_error(env, "chunk is shorter than channels * chunkLen");
+    need = (uint64_t)channels * (uint64_t)(chunk_len / hop) * (uint64_t)bins;
+    napi_get_typedarray_info(env, argv[3], &got, NULL, NULL, NULL, NULL);
+    if (got != (output == SG_OUT_U8 ? napi_uint8_array : (output == SG_OUT_RGBA8 ? napi_uint32_array : napi_float32_array)))
+      return type_error(env, "out has the wrong typed-array type for this stream's output");
+    if ((uint64_t)out_n < need) return type_error(env, "out is shorter than channels * frames * bins");
+    if (rgba && (uint64_t)rgba_n < need) return type_error(env, "outRgba is shorter than channels * frames * bins");
+  }
   rc = sg_stream_push((sg_stream*)s, (const float*)chunk, chunk_len, out, (uint32_t*)rgba);
   if (rc != SG_OK) return throw_status(env, rc);
   return undefined_of(env);
@@ -425,6 +479,11 @@ static napi_value js_ring_append(napi_env env, napi_callback_info info) {
   if (get_args(env, info, argv) < 3 || !get_external(env, argv[0], &ring)) return type_error(env, "ringAppend(ring, frames, nRows)");
   if (!get_typed(env, argv[1], napi_uint8_array, &frames, &n)) return type_error(env, "frames must be a Uint8Array");
   if (napi_get_value_int32(env, argv[2], &n_rows) != napi_ok) return type_error(env, "nRows must be an integer");
+  {
+    int bins = 0;
+    if (sg_ring_info((sg_ring*)ring, &bins, NULL) != SG_OK) return type_error(env, "ring expected");
+    if (n_rows < 0 || (uint64_t)n < (uint64_t)n_rows * (uint64_t)bins) return type_error(env, "frames is shorter than nRows * bins");
+  }
   rc = sg_ring_append((sg_ring*)ring, (const uint8_t*)frames, n_rows);
   if (rc != SG_OK) return throw_status(env, rc);
   return undefined_of(env);
@@ -575,6 +634,7 @@ napi_value napi_register_module_v1(napi_env env, napi_value exports) {
   export_fn(env, exports, "engineLastKernel", js_engine_last_kernel);
   export_fn(env, exports, "numFrames", js_num_frames);
   export_fn(env, exports, "stftBatch", js_stft_batch);
+  export_fn(env, exports, "stftBatchMulti", js_stft_batch_multi);
   export_fn(env, exports, "colormapReference", js_colormap_reference);
   export_fn(env, exports, "analyserCreate", js_analyser_create);
   export_fn(env, exports, "analyserDestroy", js_analyser_destroy);

@@ -63,6 +63,9 @@ napi_status napi_create_object(napi_env env, napi_value* result);
 napi_status napi_create_external(napi_env env, void* data, napi_finalize finalize_cb, void* finalize_hint,
                                  napi_value* result);
 napi_status napi_get_undefined(napi_env env, napi_value* result);
+napi_status napi_is_array(napi_env env, napi_value value, bool* result);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value* result);
 napi_status napi_is_typedarray(napi_env env, napi_value value, bool* result);
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type,
                                      size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);

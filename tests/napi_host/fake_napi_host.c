@@ -30,6 +30,7 @@ struct napi_value__ {
   void* fn_data;
   prop* props;
   int is_typed;
+  int is_array; size_t arr_len; napi_value* arr;     /* a JS array of values */
   napi_typedarray_type ta_type;
   size_t ta_len;
   void* ta_data;
@@ -52,6 +53,13 @@ static napi_value str(const char* s) { napi_value v = new_value(napi_string); v-
 static napi_value typed(napi_typedarray_type t, size_t len, void* data) {
   napi_value v = new_value(napi_object);
   v->is_typed = 1; v->ta_type = t; v->ta_len = len; v->ta_data = data;
+  return v;
+}
+
+static napi_value array_of(size_t n, napi_value* items) {
+  napi_value v = new_value(napi_object);
+  v->is_array = 1; v->arr_len = n; v->arr = (napi_value*)malloc(sizeof(napi_value) * (n ? n : 1));
+  memcpy(v->arr, items, sizeof(napi_value) * n);
   return v;
 }
 
@@ -118,6 +126,9 @@ napi_status napi_create_external(napi_env env, void* data, napi_finalize f, void
   return napi_ok;
 }
 napi_status napi_get_undefined(napi_env env, napi_value* r) { (void)env; *r = new_value(napi_undefined); return napi_ok; }
+napi_status napi_is_array(napi_env env, napi_value v, bool* r) { (void)env; *r = v->is_array != 0; return napi_ok; }
+napi_status napi_get_array_length(napi_env env, napi_value v, uint32_t* r) { (void)env; if (!v->is_array) return napi_array_expected; *r = (uint32_t)v->arr_len; return napi_ok; }
+napi_status napi_get_element(napi_env env, napi_value v, uint32_t i, napi_value* r) { (void)env; if (!v->is_array || i >= v->arr_len) return napi_invalid_arg; *r = v->arr[i]; return napi_ok; }
 napi_status napi_is_typedarray(napi_env env, napi_value v, bool* r) { (void)env; *r = v->is_typed != 0; return napi_ok; }
 napi_status napi_get_typedarray_info(napi_env env, napi_value v, napi_typedarray_type* type, size_t* length, void** data, napi_value* ab, size_t* off) {
   (void)env;
@@ -179,7 +190,7 @@ static napi_value options(int fft, int hop, const char* output, const char* alig
 }
 
 static void cpu_checks(void) {
-  const char* names[] = {"deviceCount", "engineCreate", "engineDestroy", "engineLastKernel", "numFrames", "stftBatch",
+  const char* names[] = {"deviceCount", "engineCreate", "engineDestroy", "engineLastKernel", "numFrames", "stftBatch", "stftBatchMulti",
                          "colormapReference", "analyserCreate", "analyserDestroy", "analyserSet", "analyserGet",
                          "analyserPush", "getByteFrequencyData", "getFloatFrequencyData", "getByteTimeDomainData",
                          "getFloatTimeDomainData", "streamCreate", "streamPush", "streamDestroy", "ringCreate", "ringAppend",
@@ -305,6 +316,71 @@ static void gpu_run(const char* out_path) {
     a7[1] = typed(napi_uint8_array, sizeof(short) * 2 * n - 1, s16);
     call("stftPcm", 7, a7);
     expect(threw("TypeError", NULL), "stftPcm with a ragged byte count -> TypeError");
+  }
+  /* clips sharded over two engines inside the library == one engine (bit for bit); array-length checks of the
+   * streaming and ring entry points (a short array must be a TypeError, never a write past its end) */
+  {
+    const int nc = 5, cl = 2048 + 37 * 512, fr = 38;
+    float* many = (float*)malloc(sizeof(float) * nc * cl);
+    unsigned char *m1 = (unsigned char*)calloc((size_t)nc * fr * bins, 1), *m2 = (unsigned char*)calloc((size_t)nc * fr * bins, 1);
+    for (int i = 0; i < nc * cl; ++i) many[i] = (float)(0.3 * sin(0.01 * i + 0.7 * (i / cl)) + 0.1 * sin(1.3 * i));
+    a[0] = num(0);
+    napi_value eng2 = call("engineCreate", 1, a);
+    napi_value pair[2] = {eng, eng2};
+    a[0] = array_of(2, pair); a[1] = typed(napi_float32_array, (size_t)nc * cl, many); a[2] = num(nc); a[3] = num(cl);
+    a[4] = options(2048, 512, "u8", "valid"); a[5] = typed(napi_uint8_array, (size_t)nc * fr * bins, m2);
+    call("stftBatchMulti", 6, a);
+    expect(!g_env.pending, "stftBatchMulti([engine, engine2], 5 clips)");
+    a[0] = eng; a[5] = typed(napi_uint8_array, (size_t)nc * fr * bins, m1);
+    call("stftBatch", 6, a);
+    expect(!g_env.pending && memcmp(m1, m2, (size_t)nc * fr * bins) == 0, "stftBatchMulti bytes == stftBatch bytes");
+    napi_value same[2] = {eng, eng};
+    a[0] = array_of(2, same);
+    call("stftBatchMulti", 6, a);
+    expect(threw("TypeError", NULL), "stftBatchMulti with one engine listed twice -> TypeError");
+    a[0] = array_of(2, pair); a[5] = typed(napi_uint8_array, (size_t)nc * fr * bins - 1, m2);
+    call("stftBatchMulti", 6, a);
+    expect(threw("TypeError", NULL), "stftBatchMulti with a short out -> TypeError");
+    a[0] = eng2;
+    call("engineDestroy", 1, a);
+    /* streaming bank: 4 channels, n_fft 1024, hop 128 */
+    a[0] = eng; a[1] = num(4); a[2] = options(1024, 128, "u8", NULL); a[3] = num(256);
+    napi_value st = call("streamCreate", 4, a);
+    expect(!g_env.pending && st->type == napi_external, "streamCreate(4 channels)");
+    float* chunk = (float*)calloc(4 * 256, sizeof(float));
+    unsigned char* so = (unsigned char*)calloc(4 * 2 * 512, 1);
+    napi_value a5[5];
+    a5[0] = st; a5[1] = typed(napi_float32_array, 4 * 256, chunk); a5[2] = num(256); a5[3] = typed(napi_uint8_array, 4 * 2 * 512, so);
+    call("streamPush", 4, a5);
+    expect(!g_env.pending, "streamPush(4 x 256 samples)");
+    a5[3] = typed(napi_uint8_array, 4 * 2 * 512 - 1, so);
+    call("streamPush", 4, a5);
+    expect(threw("TypeError", NULL), "streamPush with a short out -> TypeError");
+    a5[3] = typed(napi_uint8_array, 4 * 2 * 512, so); a5[1] = typed(napi_float32_array, 4 * 256 - 1, chunk);
+    call("streamPush", 4, a5);
+    expect(threw("TypeError", NULL), "streamPush with a short chunk -> TypeError");
+    a5[1] = typed(napi_float32_array, 4 * 256, chunk); a5[3] = typed(napi_float32_array, 4 * 2 * 512, so);
+    call("streamPush", 4, a5);
+    expect(threw("TypeError", NULL), "streamPush with a Float32Array for u8 output -> TypeError");
+    a5[3] = typed(napi_uint8_array, 4 * 2 * 512, so); a5[2] = num(100);
+    call("streamPush", 4, a5);
+    expect(threw("TypeError", NULL), "streamPush with chunkLen not a multiple of hop -> TypeError");
+    a5[2] = num(256); a5[4] = typed(napi_uint32_array, 4 * 2 * 512 - 1, so);
+    call("streamPush", 5, a5);
+    expect(threw("TypeError", NULL), "streamPush with a short outRgba -> TypeError");
+    a[0] = st;
+    call("streamDestroy", 1, a);
+    a[0] = eng; a[1] = num(512); a[2] = num(256);
+    napi_value ring = call("ringCreate", 3, a);
+    expect(!g_env.pending && ring->type == napi_external, "ringCreate(512 bins, 256 rows)");
+    a[0] = ring; a[1] = typed(napi_uint8_array, 2 * 512, so); a[2] = num(2);
+    call("ringAppend", 3, a);
+    expect(!g_env.pending, "ringAppend(2 rows)");
+    a[1] = typed(napi_uint8_array, 2 * 512 - 1, so);
+    call("ringAppend", 3, a);
+    expect(threw("TypeError", NULL), "ringAppend with frames shorter than nRows * bins -> TypeError");
+    a[0] = ring;
+    call("ringDestroy", 1, a);
   }
   FILE* f = fopen(out_path, "wb");
   fwrite(out, 1, (size_t)frames * bins, f);

@@ -383,9 +383,21 @@ def test_shard_invariance_bit_exact(engine):
     whole = engine.spectrogram(x, sg.Options())
     parts = [engine.spectrogram(x[lo:hi], sg.Options()) for lo, hi in sg.shard_bounds(13, 4)]
     assert np.array_equal(np.concatenate(parts), whole)
+    # sg_stft_batch_multi: one host thread per engine inside the library, disjoint slices of one output array
     n_dev = sg.device_count()
-    devs = list(range(n_dev)) if n_dev > 1 else [0, 0, 0]
-    assert np.array_equal(sg.spectrogram(x, devices=devs), whole)
+    if n_dev > 1:
+        assert np.array_equal(sg.spectrogram(x, devices=list(range(n_dev))), whole)
+    extra = [sg.Engine(0), sg.Engine(0)]              # three engines (here on one GPU) run their blocks concurrently
+    try:
+        for opts in (sg.Options(), sg.Options(output="db", smoothingTimeConstant=0.6)):
+            one = engine.spectrogram(x, opts)
+            assert np.array_equal(sg.spectrogram_multi([engine] + extra, x, opts), one)
+            assert np.array_equal(sg.spectrogram_multi(extra, x[:1], opts), one[:1])      # fewer clips than engines
+        with pytest.raises(TypeError):
+            sg.spectrogram_multi([engine, engine], x, sg.Options())
+    finally:
+        for e in extra:
+            e.close()
 
 
 def test_pinned_and_pageable_host_buffers_agree(engine):

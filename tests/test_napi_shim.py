@@ -31,7 +31,8 @@ def test_addon_exports_only_the_module_entry_point():
     assert "napi_register_module_v1" in names
     assert not any(n.startswith("sg_") for n in names)       # the C ABI stays in libsgcore.so
     undefined = subprocess.run(["nm", "-D", "--undefined-only", ADDON], capture_output=True, text=True).stdout
-    assert "sg_stft_batch" in undefined and "napi_create_function" in undefined
+    assert "sg_stft_batch" in undefined and "napi_create_function" in undefined and "sg_stft_batch_multi" in undefined
+    assert "sg_stream_info" in undefined and "sg_ring_info" in undefined       # array-length checks in the shim
     assert "sg_ring_view" in undefined and "sg_ring_append" in undefined
     assert "sg_wav_parse" in undefined and "sg_pcm_ingest" in undefined and "sg_stft_pcm" in undefined
 
@@ -44,7 +45,8 @@ def test_js_facade_keeps_the_analysernode_surface():
                  "set smoothingTimeConstant", "getByteFrequencyData(array)", "getFloatFrequencyData(array)",
                  "getByteTimeDomainData(array)", "getFloatTimeDomainData(array)", "createAnalyser", "connect(", "IndexSizeError",
                  "class SonogramRing", "append(frames)", "view(width, height, out)",
-                 "decodeAudioData(", "class AudioBuffer", "getChannelData(", "numberOfChannels", "spectrogramPcm("):
+                 "decodeAudioData(", "class AudioBuffer", "getChannelData(", "numberOfChannels", "spectrogramPcm(",
+                 "native.stftBatchMulti", "FinalizationRegistry", "closeAll", "OUT_CTOR[o.output]", "wholeNumber("):
         assert name in text, name
 
 
