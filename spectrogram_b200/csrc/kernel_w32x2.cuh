@@ -24,7 +24,8 @@ namespace sg {
 
 constexpr int kX2Stride = 33;                         // float2 per plane row (odd: 64-bit accesses conflict free)
 constexpr int kX2PlaneF2 = 32 * kX2Stride;            // 1056 float2 = 8448 B: exchange plane (re, then im)
-constexpr int kX2StageFloats = kW32N + 1024;          // both frames' samples when hop <= 1024
+constexpr int kX2StageFloats = kW32N + 1024 + 8;      // both frames' samples when hop <= 1024 (+ the slack of an
+                                                      // unaligned span copied from its 16-byte-aligned-down address)
 constexpr int kX2BytesStage = 2 * kW32M;              // u8 staging: 1024 (A,B) byte pairs
 constexpr int kX2WarpBytes = kX2PlaneF2 * 8 + kX2StageFloats * 4 + kX2BytesStage + 16;   // 22800 B
 constexpr int kX2Warps = 8;
@@ -154,9 +155,13 @@ struct PairGeom {
   long long clip_a, ta;    // clip and in-clip index of A
   long long clip_b, tb;
   bool has_b;
-  bool tma;                // both frames inside one clip, 16-byte aligned span, hop % 4 == 0, hop <= 1024
+  bool tma;                // both frames inside one clip, hop <= 1024 and (aligned mode) a 16-byte aligned span, hop % 4 == 0
+  int mis;                 // unaligned mode: floats between the aligned-down copy source and the span's first sample
 };
 
+// ANY_ALIGN: spans that start at any 4-byte offset (odd hops such as 441 samples = 10 ms at 44.1 kHz): the bulk copy
+// starts at the aligned-down address and the lanes read the stage at an offset
+template <bool ANY_ALIGN = false>
 __device__ __forceinline__ PairGeom make_pair(const FrameGeom& g, long long fa, long long clip_a, long long ta) {
   PairGeom p;
   p.fa = fa; p.clip_a = clip_a; p.ta = ta;
@@ -167,9 +172,17 @@ __device__ __forceinline__ PairGeom make_pair(const FrameGeom& g, long long fa, 
     else p.tb = ta + 1;
   }
   const long long start_a = g.start0 + ta * g.hop;
-  p.tma = p.has_b && p.clip_b == clip_a && g.hop <= 1024 && (g.hop & 3) == 0 && start_a >= 0 &&
-          start_a + g.hop + kW32N <= g.clip_len &&
-          ((reinterpret_cast<uintptr_t>(g.pcm + clip_a * g.clip_stride + start_a) & 15) == 0);
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(g.pcm + clip_a * g.clip_stride + start_a);
+  p.mis = (int)((addr & 15) >> 2);
+  if constexpr (ANY_ALIGN) {
+    // the copy is rounded out to 16-byte boundaries: up to 3 floats before the span (inside this clip or the
+    // previous one's tail) and up to 3 after it, which must still lie inside this clip
+    p.tma = p.has_b && p.clip_b == clip_a && g.hop <= 1024 && start_a >= 0 && start_a + g.hop + kW32N + 3 <= g.clip_len &&
+            (clip_a > 0 || start_a >= p.mis);
+  } else {
+    p.tma = p.has_b && p.clip_b == clip_a && g.hop <= 1024 && (g.hop & 3) == 0 && start_a >= 0 &&
+            start_a + g.hop + kW32N <= g.clip_len && (addr & 15) == 0;
+  }
   return p;
 }
 
@@ -185,7 +198,9 @@ __device__ __forceinline__ void window_stage1(C2& lo, C2& hi, float2 a0, float2 
 }
 
 // HOPQ > 0: hop == 64*HOPQ, so frame B's element j is the stage element j + HOPQ of the same lane and the
-// two frames share their loads (32 + HOPQ instead of 64 per lane).  HOPQ == 0: any hop.
+// two frames share their loads (32 + HOPQ instead of 64 per lane).  HOPQ == 0: any hop that is a multiple of 4
+// samples.  HOPQ < 0: any hop at all (north_star subsystem 1 for hops such as 441 samples): the bulk copy starts at
+// the span's 16-byte-aligned-down address and the lanes read the stage at the resulting offset.
 template <int OUT, int HOPQ>
 __global__ void __launch_bounds__(kX2Warps * 32, 1)
 stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
@@ -212,15 +227,18 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
   __syncthreads();
 
   // frame pair (fa, fa+1); (clip, t) advanced incrementally (no 64-bit division in the loop)
+  constexpr bool ANY = HOPQ < 0;
   const long long step = 2LL * gridDim.x * kX2Warps;
   const long long step_clip = step / g.frames_per_clip, step_t = step - step_clip * g.frames_per_clip;
-  const unsigned span_bytes = (unsigned)(kW32N + g.hop) * 4u;
+  // bytes of the bulk copy: the span itself, or (unaligned mode) the span rounded out to 16-byte boundaries
+  auto span_bytes_of = [&](const PairGeom& q) { return ANY ? (unsigned)(((kW32N + g.hop + q.mis) * 4 + 15) & ~15) : (unsigned)(kW32N + g.hop) * 4u; };
+  auto span_src_of = [&](const PairGeom& q) { return g.pcm + q.clip_a * g.clip_stride + g.start0 + q.ta * g.hop - (ANY ? q.mis : 0); };
   long long fa0 = 2 * ((long long)blockIdx.x * kX2Warps + warp);
   if (fa0 >= g.total_frames) return;
-  PairGeom cur = make_pair(g, fa0, fa0 / g.frames_per_clip, fa0 % g.frames_per_clip);
+  PairGeom cur = make_pair<ANY>(g, fa0, fa0 / g.frames_per_clip, fa0 % g.frames_per_clip);
   if (cur.tma && lane == 0) {
-    mbar_expect_tx(bar, span_bytes);
-    tma_bulk_g2s(stage, g.pcm + cur.clip_a * g.clip_stride + g.start0 + cur.ta * g.hop, span_bytes, bar);
+    mbar_expect_tx(bar, span_bytes_of(cur));
+    tma_bulk_g2s(stage, span_src_of(cur), span_bytes_of(cur), bar);
   }
   unsigned phase = 0;
 
@@ -230,7 +248,7 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
     if (nt >= g.frames_per_clip) { nt -= g.frames_per_clip; ++nclip; }
     const bool has_next = nfa < g.total_frames;
     PairGeom nxt = cur;
-    if (has_next) nxt = make_pair(g, nfa, nclip, nt);
+    if (has_next) nxt = make_pair<ANY>(g, nfa, nclip, nt);
 
     // ---- steps 1-2 (+ FFT stage 1): time blocks of both frames, window, bit-reversed into registers
     C2 a[32];
@@ -247,12 +265,23 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
           window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPQ], s[j + 16 + HOPQ], s_win[lane + 32 * j],
                         s_win[lane + 32 * (j + 16)]);
         });
-      } else {
+      } else if constexpr (HOPQ == 0) {
         const float2* sb = reinterpret_cast<const float2*>(stage + g.hop) + lane;
         static_for<0, 16>([&](auto jj) {
           constexpr int j = decltype(jj)::value;
           constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
           window_stage1(a[r0], a[r1], sa[32 * j], sa[32 * (j + 16)], sb[32 * j], sb[32 * (j + 16)],
+                        s_win[lane + 32 * j], s_win[lane + 32 * (j + 16)]);
+        });
+      } else {
+        // unaligned span: the samples sit `mis` floats into the stage and frame B another `hop` further: 4-byte reads
+        const float* fa_ = stage + cur.mis + 2 * lane;
+        const float* fb_ = fa_ + g.hop;
+        static_for<0, 16>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+          window_stage1(a[r0], a[r1], make_float2(fa_[64 * j], fa_[64 * j + 1]), make_float2(fa_[64 * (j + 16)], fa_[64 * (j + 16) + 1]),
+                        make_float2(fb_[64 * j], fb_[64 * j + 1]), make_float2(fb_[64 * (j + 16)], fb_[64 * (j + 16) + 1]),
                         s_win[lane + 32 * j], s_win[lane + 32 * (j + 16)]);
         });
       }
@@ -275,8 +304,8 @@ stft_w32x2_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::t
     __syncwarp();   // every lane has consumed the stage
     if (has_next && nxt.tma && lane == 0) {
       fence_proxy_async();   // order the generic-proxy reads above before the async-proxy overwrite
-      mbar_expect_tx(bar, span_bytes);
-      tma_bulk_g2s(stage, g.pcm + nxt.clip_a * g.clip_stride + g.start0 + nxt.ta * g.hop, span_bytes, bar);
+      mbar_expect_tx(bar, span_bytes_of(nxt));
+      tma_bulk_g2s(stage, span_src_of(nxt), span_bytes_of(nxt), bar);
     }
 
     // ---- pass 1: stages 2-5 in registers (stage 1 was fused with the window), compile-time twiddles

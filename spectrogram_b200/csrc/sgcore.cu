@@ -408,9 +408,9 @@ int launch_frames(sg_engine* e, const Plan& pl, const sg::FrameGeom& g, const sg
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2p(out_kind, v == 6 ? 8 : 12, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32x2p";
-  } else if (pl.n_fft == sg::kW32N && (v == 4 || (v == 0 && g.hop <= 1024 && (g.hop & 3) == 0)) && x2_ok) {
-    // (hops the bulk copy cannot express -- above 1024 or not a multiple of 4 samples -- are faster on the
-    // one-frame-per-warp kernel than on this kernel's guarded loads)
+  } else if (pl.n_fft == sg::kW32N && (v == 4 || (v == 0 && g.hop <= 1024)) && x2_ok) {
+    // (hops above 1024 samples -- two frames no longer fit the stage -- are faster on the one-frame-per-warp kernel
+    // than on this kernel's guarded loads; hops that are not a multiple of 4 samples take its unaligned-span form)
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
     rc = sg::launch_w32x2(out_kind, g, wp, ep, out, e->sm_count, e->device, st);
     e->last_kernel = "warp32x32x2";

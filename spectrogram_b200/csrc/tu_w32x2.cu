@@ -15,6 +15,10 @@ int launch_w32x2(int out_kind, const FrameGeom& g, const W32Plan& p, const Epilo
       rc = ensure_dynamic_smem<stft_w32x2_kernel<OUT, 8>>(kX2SmemBytes, device);
       if (rc != cudaSuccess) return (int)rc;
       stft_w32x2_kernel<OUT, 8><<<grid, kX2Warps * 32, kX2SmemBytes, st>>>(g, p, ep, (T*)out);
+    } else if ((g.hop & 3) || (g.clip_stride & 3)) {
+      rc = ensure_dynamic_smem<stft_w32x2_kernel<OUT, -1>>(kX2SmemBytes, device);
+      if (rc != cudaSuccess) return (int)rc;
+      stft_w32x2_kernel<OUT, -1><<<grid, kX2Warps * 32, kX2SmemBytes, st>>>(g, p, ep, (T*)out);
     } else {
       rc = ensure_dynamic_smem<stft_w32x2_kernel<OUT, 0>>(kX2SmemBytes, device);
       if (rc != cudaSuccess) return (int)rc;
