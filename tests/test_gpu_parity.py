@@ -128,7 +128,8 @@ def test_config4_n400_clips(engine):
 
 @pytest.mark.parametrize("n_fft,hop,kernel", [(1024, 256, "p16"), (1024, 128, "p16"), (1024, 512, "p16"), (1024, 160, "p16"), (512, 160, "p8"), (512, 128, "p8"), (512, 64, "p8"), (512, 256, "p8"), (256, 32, "p4"), (512, 100, "w16"), (256, 64, "p4"), (256, 50, "w16"),
                                                (2048, 512, "warp32x32x2p"), (2048, 256, "warp32x32x2p"),
-                                               (2048, 1024, "warp32x32x2"), (2048, 768, "warp32x32x2"), (2048, 441, "warp32x32"),
+                                               (2048, 1024, "warp32x32x2"), (2048, 768, "warp32x32x2"), (2048, 441, "warp32x32x2"), (2048, 147, "warp32x32x2"),
+                                               (2048, 1025, "warp32x32"),
                                                (4096, 1024, "eo4096"), (4096, 512, "eo4096"), (4096, 441, "wreg"), (4096, 444, "eo4096"), (4096, 4096, "eo4096")])
 @pytest.mark.parametrize("align,clip_len,n_clips", [("valid", 9000, 5), ("analyser", 4097, 3), ("valid", 2 * 8192 + 2, 1),
                                                     ("analyser", 40000, 2)])
