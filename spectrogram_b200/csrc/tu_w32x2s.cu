@@ -12,8 +12,12 @@ static int launch_xs(const FrameGeom& g, const XsGeom& x, const W32Plan& p, cons
   constexpr int smem = XsShape<NW>::kSmemBytes;
   const cudaError_t rc = ensure_dynamic_smem<stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K>>(smem, device);
   if (rc != cudaSuccess) return (int)rc;
-  stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K><<<grid, NW * 32, smem, st>>>(g, x, p, ep, (T*)out);
-  return (int)cudaGetLastError();
+  // CTAs wait for one another (a segment's first pair for its predecessor's carry): a cooperative launch guarantees
+  // that the whole grid (<= one CTA per SM) is resident at the same time, or fails instead of hanging
+  T* out_t = (T*)out;
+  void* args[] = {(void*)&g, (void*)&x, (void*)&p, (void*)&ep, (void*)&out_t};
+  return (int)cudaLaunchCooperativeKernel((const void*)stft_w32x2s_kernel<OUT, NW, HOPJ, LATE, K>, dim3(grid), dim3(NW * 32),
+                                          args, smem, st);
 }
 
 int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Plan& p, const Epilogue& ep, void* out,

@@ -22,11 +22,12 @@ ap.add_argument("--nfft", type=int, default=2048)
 ap.add_argument("--hop", type=int, default=512)
 ap.add_argument("--clip-len", type=int, default=441000)
 ap.add_argument("--window", default="blackman")
+ap.add_argument("--tau", type=float, default=0.0)
 args = ap.parse_args()
 
 eng = sg.Engine(0)
 clip_len = args.clip_len
-opts = sg.Options(fftSize=args.nfft, hop=args.hop, output=args.out, window=args.window)
+opts = sg.Options(fftSize=args.nfft, hop=args.hop, output=args.out, window=args.window, smoothingTimeConstant=args.tau)
 fpc = eng.num_frames(opts, clip_len)
 g = torch.Generator(device="cuda").manual_seed(1)
 x = (torch.rand((args.clips, clip_len), device="cuda", generator=g) - 0.5).float()
@@ -35,7 +36,7 @@ dt = torch.uint8 if args.out == "u8" else torch.float32
 bins = args.nfft // 2
 out = torch.empty((args.clips, fpc, bins), dtype=dt, device="cuda")
 WIN = {"blackman": O.WINDOW_BLACKMAN, "hann": O.WINDOW_HANN, "rect": O.WINDOW_RECT}
-ref = O.spectrogram(x[0].cpu().numpy(), O.Config(n_fft=args.nfft, hop=args.hop, window=WIN[args.window],
+ref = O.spectrogram(x[0].cpu().numpy(), O.Config(n_fft=args.nfft, hop=args.hop, window=WIN[args.window], smoothing=args.tau,
                                                  output=O.OUT_U8 if args.out == "u8" else O.OUT_F32_DB))[0]
 st = torch.cuda.Stream()
 bpf = 4 * args.hop + bins * (1 if args.out == "u8" else 4)
