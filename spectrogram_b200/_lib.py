@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgcore.so")
+# SG_LIBSGCORE selects another build of the same library (the SG_DEBUG build of tests/test_debug_build.py)
+LIB_PATH = os.environ.get("SG_LIBSGCORE") or os.path.join(_HERE, "libsgcore.so")
 
 SG_OK = 0
 SG_ERR_INVALID_ARG = -1

@@ -125,6 +125,37 @@ __device__ __forceinline__ typename OutElem<OUT>::type emit_mag(float m, const E
   }
 }
 
+// ---- SG_DEBUG build (make debug -> libsgcore_debug.so): epoch tags beside the shared-memory hand-offs.
+// compute-sanitizer is closed on this pool, so the races it would look for are checked in-tree: every value a kernel
+// passes through shared memory to another lane or warp is accompanied by a tag (in global memory, so no kernel's
+// shared-memory budget moves) holding the iteration that wrote it, and the reader asserts that it sees the tag of
+// the iteration it is in.  A missing barrier, a consumer running a pair ahead of its producer, or a stage reused
+// before it was read all show up as a tag from the wrong iteration.  tests/test_debug_build.py runs the shape list
+// of tools/sanitize_run.py through the debug library and expects zero mismatches -- and, with the turn chain of the
+// fused smoothing kernel deliberately disabled, a non-zero count (the checker does detect a real ordering bug).
+#ifdef SG_DEBUG
+constexpr int kDbgWarpSlots = 2048, kDbgMaxWarps = 16, kDbgCtaSlots = 512, kDbgSites = 16;
+struct DbgState {
+  unsigned* tags;                 // [CTA][kDbgMaxWarps][kDbgWarpSlots] then [CTA][kDbgCtaSlots]
+  unsigned long long* counts;     // [kDbgSites] mismatches per site; [kDbgSites - 1] = checks performed (per warp iteration)
+  int ctas;                       // CTAs the tag buffer was sized for
+  int break_chain;                // negative control: the fused smoothing kernel does not wait for its turn
+};
+static __device__ DbgState g_sg_dbg;   // one copy per translation unit, attached by dbg_attach()
+inline cudaError_t dbg_attach(const DbgState& st) { return cudaMemcpyToSymbol(g_sg_dbg, &st, sizeof(st)); }
+__device__ __forceinline__ unsigned* dbg_warp_tags(int warp) {
+  return g_sg_dbg.tags + ((size_t)(blockIdx.x % g_sg_dbg.ctas) * kDbgMaxWarps + warp) * kDbgWarpSlots;
+}
+__device__ __forceinline__ unsigned* dbg_cta_tags() {
+  return g_sg_dbg.tags + (size_t)g_sg_dbg.ctas * kDbgMaxWarps * kDbgWarpSlots + (size_t)(blockIdx.x % g_sg_dbg.ctas) * kDbgCtaSlots;
+}
+__device__ __forceinline__ void dbg_write(unsigned* t, int slot, unsigned epoch) { reinterpret_cast<volatile unsigned*>(t)[slot] = epoch; }
+__device__ __forceinline__ void dbg_check(const unsigned* t, int slot, unsigned epoch, int site) {
+  if (reinterpret_cast<const volatile unsigned*>(t)[slot] != epoch) atomicAdd(g_sg_dbg.counts + site, 1ull);
+}
+__device__ __forceinline__ void dbg_count_iteration() { atomicAdd(g_sg_dbg.counts + kDbgSites - 1, 1ull); }
+#endif
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }

@@ -206,7 +206,15 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
 #ifdef SG_XP_TRACE
   int trace_iter = 0;
 #endif
+#ifdef SG_DEBUG
+  unsigned dbg_epoch = 0;                       // this warp's pair counter
+  unsigned* dbg_tags = dbg_warp_tags(warp);     // [0, 1024): exchange elements (writer lane, q); [1024, 2048): byte-stage entries
+#endif
   while (true) {
+#ifdef SG_DEBUG
+    ++dbg_epoch;
+    if (lane == 0) dbg_count_iteration();
+#endif
     XP_TRACE(0);
     // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
     C2 a[32];
@@ -258,6 +266,9 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         constexpr int q = decltype(qq)::value;
         wre[2 * q] = a[q].re.v;
         wim[2 * q] = a[q].im.v;
+#ifdef SG_DEBUG
+        dbg_write(dbg_tags, lane * 32 + q, dbg_epoch);
+#endif
       });
       asm volatile("bar.sync %0, 32;" ::"r"(warp + 1) : "memory");
       XP_TRACE(2);
@@ -269,6 +280,11 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         const float4 vr = rre[j * kXpStride], vi = rim[j * kXpStride];
         a[q0].re = P2(vr.x, vr.y); a[q0 + 16].re = P2(vr.z, vr.w);
         a[q0].im = P2(vi.x, vi.y); a[q0 + 16].im = P2(vi.z, vi.w);
+#ifdef SG_DEBUG
+        // rows 2j and 2j + 1 of column `lane`: written by lanes 2j, 2j + 1 as their element `lane`, this iteration
+        dbg_check(dbg_tags, (2 * j) * 32 + lane, dbg_epoch, 0);
+        dbg_check(dbg_tags, (2 * j + 1) * 32 + lane, dbg_epoch, 0);
+#endif
       });
       __syncwarp();
     }
@@ -369,6 +385,10 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
         } else if constexpr (OUT == kOutU8) {
           sb16[k] = (uint16_t)__byte_perm(ka, kb, 0x0040);     // one PRMT instead of SHF + LOP3
           sb16[mk] = (uint16_t)__byte_perm(ma, mb, 0x0040);
+#ifdef SG_DEBUG
+          dbg_write(dbg_tags, 1024 + k, dbg_epoch);
+          dbg_write(dbg_tags, 1024 + mk, dbg_epoch);
+#endif
         } else {
           row_a[k] = __ldg(ep.lut + ka); row_a[mk] = __ldg(ep.lut + ma);
           if (has_b_out) { row_b[k] = __ldg(ep.lut + kb); row_b[mk] = __ldg(ep.lut + mb); }
@@ -383,6 +403,9 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint4 w = s16[c * 32 + lane];
+#ifdef SG_DEBUG
+          for (int e8 = 0; e8 < 8; ++e8) dbg_check(dbg_tags, 1024 + 8 * (c * 32 + lane) + e8, dbg_epoch, 1);
+#endif
           ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
           if (has_b_out) rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
         }

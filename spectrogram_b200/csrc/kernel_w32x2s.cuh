@@ -171,6 +171,10 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
   }
 
+#ifdef SG_DEBUG
+  unsigned dbg_q = warp;                        // this pair's place in the CTA's pair sequence (round robin over warps)
+  unsigned* dbg_tags = dbg_cta_tags();          // one tag per state slot (i, lane): the pair that wrote it, plus one
+#endif
   while (true) {
     const XsItem cur = xs_item(x, fpc, it);
     const int ta = cur.f0 + 2 * p;
@@ -304,7 +308,15 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     }
     static_for<0, K>([&](auto cc) {
       constexpr int c = decltype(cc)::value, i0 = c * (16 / K), i1 = i0 + 16 / K;
+#ifdef SG_DEBUG
+      if (!g_sg_dbg.break_chain)
+#endif
       while (!mbar_try_wait(s_bar + c * NW + warp, turn)) {}
+#ifdef SG_DEBUG
+      if (lane == 0 && c == 0) dbg_count_iteration();
+      // every slot of this group must hold the state the pair just before this one left (or this pair's own start state)
+      if (p != 0) static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_check(dbg_tags, i * 32 + lane, dbg_q, 2); });
+#endif
       if (p == 0) {
         // first pair of a work item: the state the segment starts from
         const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
@@ -370,10 +382,17 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
           s_state[i * 32 + lane] = make_float2(nk, nm);
         });
       }
+#ifdef SG_DEBUG
+      static_for<i0, i1>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_write(dbg_tags, i * 32 + lane, dbg_q + 1); });
+      __threadfence_block();
+#endif
       __syncwarp();
       if (lane0) mbar_arrive(s_bar + c * NW + (warp + 1 == NW ? 0 : warp + 1));
     });
     turn ^= 1;
+#ifdef SG_DEBUG
+    dbg_q += NW;
+#endif
     const bool last = p == (cur.nfr + 1) / 2 - 1;
     if (last && !(cur.kind == 2 && cur.seg + 1 < x.segs)) {
       // last pair of a work item: hand the state to the next segment (or to the caller)

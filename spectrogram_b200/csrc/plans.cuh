@@ -109,6 +109,11 @@ struct PcmMix;
 int pcm_tile_frames(int bytes_per_frame);
 int launch_pcm_ingest(int format, const PcmGeom& g, long long n_clips, const PcmMix& m, cudaStream_t st);
 
+#ifdef SG_DEBUG
+int dbg_attach_w32x2p(const DbgState& st);
+int dbg_attach_w32x2s(const DbgState& st);
+#endif
+
 constexpr int kMaxDevices = 64;
 
 // one cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per kernel per device

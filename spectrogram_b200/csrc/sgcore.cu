@@ -351,6 +351,9 @@ struct sg_engine {
   // The scratch buffers above (smoothing state, magnitude tiles, carry vectors, the custom colour table) are shared by
   // every call on this engine, whatever stream the caller passes.  A call that uses them first makes its stream wait
   // for the previous user's last kernel and records its own end on this event afterwards.
+#ifdef SG_DEBUG
+  sg::DbgState dbg{};                // epoch-tag buffers of the SG_DEBUG build (common.cuh)
+#endif
   cudaEvent_t ev_scratch = nullptr;
   cudaEvent_t ev_ring_in[4] = {}, ev_ring_k[4] = {}, ev_pin_in[2] = {}, ev_pin_out[2] = {};   // sg_stft_batch's pipeline
   bool scratch_busy = false;
@@ -729,6 +732,20 @@ int sg_engine_create(int device, sg_engine** out) {
     reference_lut(lut);
     SG_CUDA(cudaMalloc((void**)&e->lut_ref, sizeof(lut)));
     SG_CUDA(cudaMemcpy(e->lut_ref, lut, sizeof(lut), cudaMemcpyHostToDevice));
+#ifdef SG_DEBUG
+    {
+      const size_t words = (size_t)e->sm_count * (sg::kDbgMaxWarps * sg::kDbgWarpSlots + sg::kDbgCtaSlots);
+      SG_CUDA(cudaMalloc((void**)&e->dbg.tags, words * sizeof(unsigned)));
+      SG_CUDA(cudaMemset(e->dbg.tags, 0, words * sizeof(unsigned)));
+      SG_CUDA(cudaMalloc((void**)&e->dbg.counts, sg::kDbgSites * sizeof(unsigned long long)));
+      SG_CUDA(cudaMemset(e->dbg.counts, 0, sg::kDbgSites * sizeof(unsigned long long)));
+      e->dbg.ctas = e->sm_count;
+      const char* brk = getenv("SG_DEBUG_BREAK_CHAIN");
+      e->dbg.break_chain = brk && brk[0] == '1';
+      SG_CUDA((cudaError_t)sg::dbg_attach_w32x2p(e->dbg));
+      SG_CUDA((cudaError_t)sg::dbg_attach_w32x2s(e->dbg));
+    }
+#endif
     return SG_OK;
   }();
   if (rc != SG_OK) {          // nothing half-built is left behind
@@ -998,6 +1015,19 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
   return rc;
 }
 }  // namespace
+
+#ifdef SG_DEBUG
+// debug build only (not part of include/sgcore.h): mismatches per check site -- 0 exchange planes of the frame-pair
+// kernel, 1 its byte stage, 2 the state hand-off of the fused smoothing kernel -- and, in the last entry, how many
+// warp iterations ran with the checks armed
+extern "C" int sg_debug_counts(sg_engine* e, unsigned long long out[16]) {
+  if (!e || !out) return fail(SG_ERR_INVALID_ARG, "null argument");
+  SG_CUDA(cudaSetDevice(e->device));
+  SG_CUDA(cudaDeviceSynchronize());
+  SG_CUDA(cudaMemcpy(out, e->dbg.counts, sg::kDbgSites * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SG_OK;
+}
+#endif
 
 extern "C" {
 int sg_stft_batch(sg_engine* e, const float* pcm, int64_t n_clips, int64_t clip_len, const sg_stft_config* cfg,

@@ -34,4 +34,8 @@ int launch_w32x2p(int out_kind, int warps, const FrameGeom& g, const W32Plan& p,
   });
 }
 
+#ifdef SG_DEBUG
+int dbg_attach_w32x2p(const DbgState& st) { return (int)dbg_attach(st); }
+#endif
+
 }  // namespace sg

@@ -33,4 +33,8 @@ int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Pl
   });
 }
 
+#ifdef SG_DEBUG
+int dbg_attach_w32x2s(const DbgState& st) { return (int)dbg_attach(st); }
+#endif
+
 }  // namespace sg

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""One small call into every kernel family, for compute-sanitizer:
-   compute-sanitizer --tool memcheck  python tools/sanitize_run.py
-   compute-sanitizer --tool racecheck python tools/sanitize_run.py"""
+"""One small call into every kernel family and every object of the C ABI.  Run against the SG_DEBUG build of the
+library (make -C spectrogram_b200/csrc debug; SG_LIBSGCORE=spectrogram_b200/libsgcore_debug.so) it arms the epoch
+tags beside the shared-memory hand-offs (spectrogram_b200/csrc/common.cuh) and prints the mismatch counts as a JSON
+line; tests/test_debug_build.py drives it that way.  (compute-sanitizer is closed on this pool.)"""
+import ctypes as C
+import json
 import os
 import sys
 
@@ -41,5 +44,22 @@ an.push(x[0, :4096])
 buf = np.zeros(an.frequencyBinCount, np.uint8)
 an.getByteFrequencyData(buf)
 an.close()
+# larger batches: every warp of every CTA runs several pairs, clips end inside CTAs, and the fused smoothing kernel runs in
+# both of its modes (chained segments, look-back)
+big = (0.1 * rng.standard_normal((160, 2048 + 90 * 512))).astype(np.float32)
+for out in ("u8", "db"):
+    eng.spectrogram(big, sg.Options(output=out))
+    seen.add(eng.last_kernel)
+eng.set_kernel_variant(7)
+for clips in (160, 3):
+    eng.spectrogram(big[:clips], sg.Options(smoothingTimeConstant=0.8))
+    seen.add(eng.last_kernel)
+eng.set_kernel_variant(0)
+lib = sg._lib.load()
+if hasattr(lib, "sg_debug_counts"):
+    counts = (C.c_ulonglong * 16)()
+    lib.sg_debug_counts.argtypes = [C.c_void_p, C.c_void_p]
+    assert lib.sg_debug_counts(eng.handle, counts) == 0
+    print(json.dumps({"debug_counts": list(counts), "kernels": sorted(seen)}))
 eng.close()
 print("sanitize_run ok; kernels:", sorted(seen))
