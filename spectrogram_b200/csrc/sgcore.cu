@@ -889,9 +889,9 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
     state = (float*)e->scratch_state.p;
   }
   const bool in_pinned = is_pinned(pcm), out_pinned = is_pinned(out);
-  // target bytes per chunk, whichever side (input or output) is larger: at small hops a frame's output dwarfs its hop.
-  // Raw 16-bit PCM moves half the input bytes per sample: larger chunks keep its copies as long as the float path's.
-  const size_t kChunk = (raw ? 64u : 32u) << 20;
+  // target bytes per chunk, whichever side (input or output) is larger: at small hops a frame's output dwarfs its hop
+  static const size_t kChunkEnv = [] { const char* v = getenv("SG_CHUNK_MB"); return (size_t)(v ? atoi(v) : 0) << 20; }();
+  const size_t kChunk = kChunkEnv ? kChunkEnv : (size_t)32 << 20;
   struct Chunk { long long c0, nc, t0, nt; };
   std::vector<Chunk> chunks;
   const size_t clip_bytes = (size_t)clip_len * unit;
