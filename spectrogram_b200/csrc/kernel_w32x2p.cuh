@@ -129,7 +129,7 @@ __device__ __forceinline__ bool pair_is_fast(const FrameGeom& g, const PairP& p,
 // ABL (tools/microbench/ablate_bench.cu only; 0 in every product launch) removes one component at a time -- results are
 // wrong, the time saved is that component's marginal cost under the real contention: 1 exchange, 2 mirror shuffles,
 // 4 MUFU/F2IP, 8 next-pair loads, 16 byte stage + row stores, 32 window table reads, 64 lane-0 selects (128: the
-// selects as PRMT instead of FSEL)
+// selects as PRMT instead of FSEL; 256: the mirrors through shared memory instead of shuffles)
 template <int OUT, int NW, int HOPJ = 8, int ABL = 0>   // hop = 64 * HOPJ samples: frame B's element j is element j + HOPJ of the lane
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out, int stagger) {
@@ -314,6 +314,25 @@ stft_w32x2p_kernel(FrameGeom g, W32Plan pl, Epilogue ep, typename OutElem<OUT>::
     //      a[32 - i] intact until it is read), so the arithmetic below is pure register work with no shuffle in
     //      its dependency chains.  Bin 512 = conj Z[512] (lane 0's a[16]) is taken before a[16] is replaced.
     const P2 p512 = mul2(bc(4.f), fma2(a[16].re, a[16].re, mul2(a[16].im, a[16].im)));
+    if constexpr (ABL & 256) {
+      // experiment: the mirrors through the (idle) exchange planes instead of shuffles + lane-0 selects: 32 STS.64 +
+      // 32 LDS.64 (128 wavefronts) instead of 64 SHFL (64 wavefronts) + 64 FSEL; lane 0's case is just an address
+      float2* xre = reinterpret_cast<float2*>(xp);
+      float2* xim = xre + 520;
+      static_for<16, 32>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        xre[lane + 32 * (i - 16)] = a[i].re.v;
+        xim[lane + 32 * (i - 16)] = a[i].im.v;
+      });
+      if (lane0) { xre[512] = a[0].re.v; xim[512] = a[0].im.v; }
+      __syncwarp();
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        a[31 - i].re = P2(xre[512 - lane - 32 * i]);
+        a[31 - i].im = P2(xim[512 - lane - 32 * i]);
+      });
+      __syncwarp();
+    } else
     static_for<0, 16>([&](auto ii) {
       constexpr int i = 15 - decltype(ii)::value;
       constexpr int src = 31 - i, own = (32 - i) & 31;

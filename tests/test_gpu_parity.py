@@ -649,3 +649,26 @@ def test_fused_smoothing_non_finite_frames_reset_the_state(engine):
         bad = np.all(ref[c] == 0, axis=1)
         assert bad.sum() == 4 and np.all(got[c][bad] == 0)
     assert_mag_close(got, ref)
+
+
+def test_fused_smoothing_kernel_on_frame_ranges_of_a_long_clip(engine):
+    """The host entry cuts one long clip into frame ranges and chains them through the per-clip state: the fused kernel
+    (forced: one clip is below its automatic threshold) must pick the state up and write rows at the range's offset."""
+    rng = np.random.default_rng(21)
+    x = (0.1 * rng.standard_normal(44100 * 240)).astype(np.float32)      # 42 MB > one 32 MB chunk
+    opts = sg.Options(fftSize=2048, hop=512, output="mag", smoothingTimeConstant=0.8)
+    engine.set_kernel_variant(7)
+    try:
+        got = engine.spectrogram(x, opts)
+    finally:
+        engine.set_kernel_variant(0)
+    assert engine.last_kernel == "warp32x32x2s"
+    per = (32 << 20) // (512 * 4)                     # frames per chunk of the host pipeline
+    assert got.shape[0] > per + 100
+    lo = per - 200
+    seg = x[lo * 512: (per + 60) * 512 + 2048]
+    ref = O.spectrogram(seg, O.Config(n_fft=2048, hop=512, smoothing=0.8, output=O.OUT_F32_MAG))[0]
+    assert_mag_close(got[lo + 150: per + 60], ref[150:260])              # 150 frames of warm-up: 0.8^150 ~ 3e-15
+    two = engine.spectrogram(x, opts)                                     # automatic: the two-kernel path
+    assert engine.last_kernel != "warp32x32x2s"
+    assert np.all(np.abs(two - got) <= 2e-5 * np.abs(got) + 1e-7 * got.max(axis=-1, keepdims=True))

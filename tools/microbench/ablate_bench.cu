@@ -48,6 +48,7 @@ int main() {
         Epilogue{3.0103f, -72.f, 10.97f, 100.f, 364.f, 1.f / 4096, nullptr}, out, (long long)n_clips * fpc};
   run<0>(c, "full kernel");
   run<128>(c, "full kernel, lane-0 selects as PRMT");
+  run<256>(c, "full kernel, mirrors through shared memory");
   run<0>(c, "full kernel (again)");
   run<1>(c, "- exchange (STS/bar/LDS)");
   run<2>(c, "- mirror shuffles");
