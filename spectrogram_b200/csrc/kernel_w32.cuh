@@ -57,6 +57,20 @@ __device__ __forceinline__ void bfly_const(float2& x, float2& y) {
   }
 }
 
+// (wx, wy) = W_N^P * base, reusing W^{P + N/4} = -i W^P
+template <int P, int N>
+__device__ __forceinline__ float2 twiddle_times(float2 b) {
+  if constexpr (P == 0) {
+    return b;
+  } else if constexpr (4 * P >= N) {
+    const float2 t = twiddle_times<P - N / 4, N>(b);
+    return make_float2(t.y, -t.x);
+  } else {
+    constexpr float cx = Twiddle<P, N>::re, cy = Twiddle<P, N>::im;
+    return make_float2(fmaf(cx, b.x, -cy * b.y), fmaf(cx, b.y, cy * b.x));
+  }
+}
+
 // stages 1..5 of a radix-2 DIT network on 32 register-resident points (input bit-reversed)
 template <int S>
 __device__ __forceinline__ void dit_stage_const(float2 (&a)[32]) {

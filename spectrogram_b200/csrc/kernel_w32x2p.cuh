@@ -61,20 +61,6 @@ struct XpShape {
   static constexpr int kMaxRegs = NW <= 8 ? 255 : (65536 / (NW * 32)) / 8 * 8;
 };
 
-// (wx, wy) = W_N^P * base, reusing W^{P + N/4} = -i W^P
-template <int P, int N>
-__device__ __forceinline__ float2 twiddle_times(float2 b) {
-  if constexpr (P == 0) {
-    return b;
-  } else if constexpr (4 * P >= N) {
-    const float2 t = twiddle_times<P - N / 4, N>(b);
-    return make_float2(t.y, -t.x);
-  } else {
-    constexpr float cx = Twiddle<P, N>::re, cy = Twiddle<P, N>::im;
-    return make_float2(fmaf(cx, b.x, -cy * b.y), fmaf(cx, b.y, cy * b.x));
-  }
-}
-
 // stage U (1..5) of pass 2: butterflies (i0, i0 + half), twiddle W_{2 half}^p * base
 template <int U>
 __device__ __forceinline__ void dit2_stage_gen(C2 (&a)[32], float2 base) {

@@ -72,18 +72,28 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
     else asm volatile("bar.sync %0, %1;" ::"r"(fs + 1), "n"(T) : "memory");
   };
   const long long groups = (g.total_frames + S::FPC - 1) / S::FPC;
-  for (long long gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+  // where a frame slot's samples are: clip base, first sample, and whether the 8-byte loader can take them
+  struct Src { const float* x; long long start, fc; bool live, interior; };
+  auto source_of = [&](long long gi) {
+    Src r;
     const long long f = gi * S::FPC + fs;
-    const bool live = f < g.total_frames;
-    const long long fc = live ? f : g.total_frames - 1;     // idle slots recompute the last frame, store nothing
-    const long long clip = fc / g.frames_per_clip, tt = fc - clip * g.frames_per_clip;
-    const long long start = g.start0 + tt * g.hop;
-    const float* __restrict__ x = g.pcm + clip * g.clip_stride;
+    r.live = f < g.total_frames;
+    r.fc = r.live ? f : g.total_frames - 1;                 // idle slots recompute the last frame, store nothing
+    const long long clip = r.fc / g.frames_per_clip, tt = r.fc - clip * g.frames_per_clip;
+    r.start = g.start0 + tt * g.hop;
+    r.x = g.pcm + clip * g.clip_stride;
+    r.interior = r.start >= 0 && r.start + N <= g.clip_len && ((reinterpret_cast<uintptr_t>(r.x + r.start) & 7) == 0);
+    return r;
+  };
+  for (long long gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    const Src cur = source_of(gi);
+    const bool live = cur.live, interior = cur.interior;
+    const long long fc = cur.fc, start = cur.start;
+    const float* __restrict__ x = cur.x;
     const float2* __restrict__ win2 = reinterpret_cast<const float2*>(pl.win);
 
     // ---- pass 1: load + window + stages 1-5
     float2 v[32];
-    const bool interior = start >= 0 && start + N <= g.clip_len && ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
     if (interior) {
       const float2* __restrict__ src = reinterpret_cast<const float2*>(x + start) + t;
       static_for<0, 32>([&](auto jj) {
@@ -214,7 +224,24 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
         static_for<0, S::G2>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
           const int ka = (R > 5) ? (t & 31) : (t + T * c);
-          dit_stages_table<R2, c * S::S2, 32>(v, pl.tw2 + ka);
+          if constexpr (R2 == 5) {
+            // twiddles of a stage from its per-column base (row 2^(u-1) - 1) times compile-time roots: FP32-pipe work
+            // instead of 31 table loads per thread (the L1 data pipe is this kernel's busiest unit)
+            static_for<1, 6>([&](auto uu) {
+              constexpr int u = decltype(uu)::value, half = 1 << (u - 1);
+              const float2 base = __ldg(pl.tw2 + (half - 1) * 32 + ka);
+              static_for<0, half>([&](auto pp) {
+                constexpr int p = decltype(pp)::value;
+                const float2 w = twiddle_times<p, 2 * half>(base);
+                static_for<0, 16 / half>([&](auto bb) {
+                  constexpr int i0 = decltype(bb)::value * 2 * half + p;
+                  bfly(v[i0], v[i0 + half], w.x, w.y);
+                });
+              });
+            });
+          } else {
+            dit_stages_table<R2, c * S::S2, 32>(v, pl.tw2 + ka);
+          }
         });
         static_for<0, S::G2>([&](auto cc) {
           constexpr int c = decltype(cc)::value;
@@ -227,34 +254,93 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
         frame_sync();
       }
 
-      // ---- pass 3: stages 11 .. 10+R3; sub-FFT c: column k_a, q = g*G3 + c, rows bitrev5(q)*L2 + bitrev(h)
       if constexpr (R3 > 0) {
-        const int ka = t & 31, gq = t >> 5;
-        const int brg = (int)(__brev((unsigned)gq) >> (32 - R3));
-        static_for<0, S::G3>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;   // bitrev5(gq*G3 + c) * L2
-          static_for<0, S::S3>([&](auto hh) {
+        // ---- pass 3 (stages 11 .. 10+R3) merged with the untangle.  A sub-FFT is (column c, q): the S3 points
+        //      Z[c + 32 (q + 32 h)], h < S3, read from rows bitrev5(q)*S3 + bitrev(h).  The mirror of that bin is
+        //      (column 32 - c, 31 - q, S3-1 - h), so thread (pi = t & 15, qg = t >> 4) takes the column pair
+        //      (pi, 32 - pi) and, in each, the q's {j, 31 - j : j in its range}: every Z[k] meets Z[M - k] in the same
+        //      thread's registers -- no write-back of pass 3, no second read of the tile.  Pair 0 is the two
+        //      self-mirrored columns: 16 (q <-> 31 - q) and 0 (q <-> 32 - q, with q = 0 and q = 16 mirrored onto
+        //      themselves).  tools/emulate_wreg.py (merged_pass3) checks this index algebra.
+        constexpr int S3 = S::S3, NP = 16 / (T / 16), NQ = 2 * NP;
+        const int pi = t & 15, qg = t >> 4;
+        const bool self = pi == 0, self0 = self && qg == 0;
+        const int col[2] = {pi, self ? 16 : 32 - pi};
+        int qs[2][NQ];
+        static_for<0, NP>([&](auto ss) {
+          constexpr int sl = decltype(ss)::value;
+          const int j = qg * NP + sl;
+          qs[0][2 * sl] = j;
+          qs[0][2 * sl + 1] = self ? (j == 0 ? 16 : 32 - j) : 31 - j;
+          qs[1][2 * sl] = self ? j : 31 - j;
+          qs[1][2 * sl + 1] = self ? 31 - j : j;
+        });
+        static_for<0, 2 * NQ>([&](auto ee) {
+          constexpr int e = decltype(ee)::value, xx = e / NQ, i = e % NQ;
+          const int q = qs[xx][i];
+          const float2* src = A + (int)(__brev((unsigned)q) >> 27) * S3 * kWregStride + col[xx];
+          static_for<0, S3>([&](auto hh) {
             constexpr int h = decltype(hh)::value;
-            v[c * S::S3 + h] = A[(row0 + bitrev(h, R3)) * kWregStride + ka];
+            v[e * S3 + h] = src[bitrev(h, R3) * kWregStride];
           });
         });
-        static_for<0, S::G3>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          const int q = gq * S::G3 + c;
-          dit_stages_table<R3, c * S::S3, 32>(v, pl.tw3 + (q * (S::S3 - 1)) * 32 + ka);
+        static_for<0, 2 * NQ>([&](auto ee) {
+          constexpr int e = decltype(ee)::value, xx = e / NQ, i = e % NQ;
+          const float2* tw = pl.tw3 + (qs[xx][i] * (S3 - 1)) * 32 + col[xx];
+          const float2 w0 = __ldg(tw);                          // stage 11: W_2048^{32 q + c}
+          if constexpr (S3 == 2) {
+            bfly(v[e * 2], v[e * 2 + 1], w0.x, w0.y);
+          } else {
+            const float2 w1 = __ldg(tw + 32);                   // stage 12: W_4096^{32 q + c}; p = 1 is -i times it
+            bfly(v[e * 4], v[e * 4 + 1], w0.x, w0.y);
+            bfly(v[e * 4 + 2], v[e * 4 + 3], w0.x, w0.y);
+            bfly(v[e * 4], v[e * 4 + 2], w1.x, w1.y);
+            bfly(v[e * 4 + 1], v[e * 4 + 3], w1.y, -w1.x);
+          }
         });
-        static_for<0, S::G3>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
-          const int row0 = (bitrev(c, 5 - R3) * S::S3 + brg) * L2;
-          static_for<0, S::S3>([&](auto hh) {
+        // now v[(x NQ + i) S3 + h] = Z[col[x] + 32 (qs[x][i] + 32 h)]
+        const bool bad = !(fabsf(v[0].x) <= 3.4028235e38f) || !(fabsf(v[0].y) <= 3.4028235e38f);
+        static_for<0, 2 * NQ>([&](auto ee) {
+          constexpr int e = decltype(ee)::value, xx = e / NQ, i = e % NQ;
+          static_for<0, S3 / 2>([&](auto hh) {
             constexpr int h = decltype(hh)::value;
-            A[(row0 + bitrev(h, R3)) * kWregStride + ka] = v[c * S::S3 + h];
+            const int k = col[xx] + 32 * (qs[xx][i] + 32 * h);
+            const float2 zk = v[e * S3 + h];
+            float2 zm = v[((1 - xx) * NQ + i) * S3 + (S3 - 1 - h)];
+            const float2 zs = v[(xx * NQ + (i ^ 1)) * S3 + (S3 - 1 - h)];
+            zm.x = self ? zs.x : zm.x;
+            zm.y = self ? zs.y : zm.y;
+            if constexpr (xx == 0 && i < 2) {
+              const float2 z0 = v[i * S3 + (i == 0 ? (S3 - h) % S3 : S3 - 1 - h)];
+              zm.x = self0 ? z0.x : zm.x;
+              zm.y = self0 ? z0.y : zm.y;
+            }
+            const float2 w = __ldg(pl.ut + k);
+            const float ex = zk.x + zm.x, ey = zk.y - zm.y;       // 2E
+            const float ox = zk.y + zm.y, oy = zm.x - zk.x;       // 2O
+            const float xr = fmaf(ox, w.x, fmaf(-oy, w.y, ex));   // 2X[k]
+            const float xi = fmaf(ox, w.y, fmaf(oy, w.x, ey));
+            const float yr = fmaf(2.f, ex, -xr);                  // 2 conj X[M-k]
+            const float yi = fmaf(2.f, ey, -xi);
+            const float pk = bad ? 0.f : fmaf(xr, xr, xi * xi);
+            float pm = bad ? 0.f : fmaf(yr, yr, yi * yi);
+            int mk = M - k;
+            if constexpr (e == 0 && h == 0) {
+              // the mirror of k = 0 is the dropped Nyquist bin; the slot carries bin M/2 = conj Z[M/2]
+              const float2 zh = v[S3 / 2];
+              mk = self0 ? M / 2 : mk;
+              pm = self0 ? (bad ? 0.f : 4.f * fmaf(zh.x, zh.x, zh.y * zh.y)) : pm;
+            }
+            if constexpr (OUT == kOutU8) {
+              sb[k] = emit_power_finite<OUT>(pk, ep);
+              sb[mk] = emit_power_finite<OUT>(pm, ep);
+            } else if (live) {
+              row[k] = emit_power_finite<OUT>(pk, ep);
+              row[mk] = emit_power_finite<OUT>(pm, ep);
+            }
           });
         });
-        frame_sync();
-      }
-
+      } else {
       // ---- untangle + epilogue: thread t owns k = t + T i (i < 16) and the mirror bins M - k
       auto zat = [&](int k) { return A[(int)(__brev((unsigned)(k >> 5)) >> (32 - R)) * kWregStride + (k & 31)]; };
       // [SPEC] "non-finite -> 0" decided once per frame: a non-finite sample makes EVERY Z of its frame non-finite
@@ -294,6 +380,7 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
           row[mk] = emit_power_finite<OUT>(pm, ep);
         }
       });
+      }
     }
     frame_sync();
     if constexpr (OUT == kOutU8) {
