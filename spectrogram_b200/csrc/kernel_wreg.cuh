@@ -5,12 +5,23 @@
 // M = n_fft/2 complex points, T = M/32 threads per frame, 32 points per thread.  The network is
 // radix-2 decimation in time; its log2(M) stages are run in up to three register passes
 //   pass 1  stages 1-5      thread b owns z[b + T j], j < 32; compile-time twiddles
-//   pass 2  stages 6-10     min(log2(M)-5, 5) stages; lane-major twiddle table W_{32*2^u}^{32 p + k_a}
-//   pass 3  stages 11-12    only M = 2048, 4096
+//   pass 2  stages 6-10     min(log2(M)-5, 5) stages; lane-major twiddle table W_{32*2^u}^{32 p + k_a} (all 5 stages:
+//                           only the per-column base of each stage is loaded, the rest are compile-time roots times it)
+//   pass 3  stages 11-12    only M = 2048, 4096; merged with the untangle: a thread takes a column pair (c, 32 - c) and
+//                           the q's whose mirrors it also holds, so Z[k] and Z[M - k] meet in its registers and pass 3
+//                           is neither written back nor read again
 // with the frame's working set in one shared-memory tile A[row][col], row stride 33 float2, updated in
-// place between passes (every access pattern below is bank-conflict free: lanes always walk a row).
-// After the last pass Z[k] sits at A[bitrev(k >> 5)][k & 31]; the real-input untangle, |X|^2, dB and
-// byte/colour epilogue follow as in kernel_w32.cuh.  tools/emulate_wreg.py checks the index algebra.
+// place between passes (lanes always walk a row: conflict free but for the one lane of a half-warp that owns the
+// self-mirrored columns 0 and 16).  Without pass 3, Z[k] sits at A[bitrev(k >> 5)][k & 31] after the last pass; the
+// real-input untangle, |X|^2, dB and byte/colour epilogue follow as in kernel_w32.cuh.  tools/emulate_wreg.py checks the
+// index algebra of both forms.
+//
+// n_fft 8192 on a B200 (64 clips x 60 s, byte rows): 76 M frames/s with pass 3 written back and table twiddles (L1 data
+// pipe 77 % busy: 2 900 wavefronts per frame), 87 M as it stands (1 830 wavefronts, issue slots 64 % busy, FP32 pipe 48 %).
+// Measured and rejected: the next frame's samples prefetched into registers behind the epilogue (128 registers do not
+// hold them: spills, 66 M); FFMA2-packed butterflies on (element i, element i + 16) register pairs (17 % fewer
+// instructions, but word-wide tile accesses and twiddle loads double the LSU instructions, and the dependent packed chains
+// stall: 71 M).
 //
 // Frames of a CTA (256 threads = 256/T frames) advance together; for T <= 32 a frame lives inside one
 // warp and only __syncwarp() is needed.
@@ -272,8 +283,8 @@ stft_wreg_kernel(FrameGeom g, WregPlan pl, Epilogue ep, typename OutElem<OUT>::t
           const int j = qg * NP + sl;
           qs[0][2 * sl] = j;
           qs[0][2 * sl + 1] = self ? (j == 0 ? 16 : 32 - j) : 31 - j;
-          qs[1][2 * sl] = self ? j : 31 - j;
-          qs[1][2 * sl + 1] = self ? 31 - j : j;
+          qs[1][2 * sl] = 31 - j;      // (column 16 mirrors slot 2s onto 2s+1 in either order: keep the rows of the
+          qs[1][2 * sl + 1] = j;       //  other lanes, so its reads fall into the bank the half-warp leaves free)
         });
         static_for<0, 2 * NQ>([&](auto ee) {
           constexpr int e = decltype(ee)::value, xx = e / NQ, i = e % NQ;

@@ -119,7 +119,7 @@ def merged_pass3(log2m, A, z):
             j = qg * NP + s
             if self_:
                 q[0][2 * s], q[0][2 * s + 1] = j, (16 if j == 0 else 32 - j)
-                q[1][2 * s], q[1][2 * s + 1] = j, 31 - j
+                q[1][2 * s], q[1][2 * s + 1] = 31 - j, j
             else:
                 q[0][2 * s], q[0][2 * s + 1] = j, 31 - j
                 q[1][2 * s], q[1][2 * s + 1] = 31 - j, j
