@@ -76,7 +76,14 @@ int launch_pair_l4(int out_kind, const FrameGeom& g, const PairPlan& p, const Ep
 int launch_pair_l3(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
                    int device, cudaStream_t st);   // n_fft 512
 int launch_pair_l2(int out_kind, const FrameGeom& g, const PairPlan& p, const Epilogue& ep, void* out, int sm_count,
-                   int device, cudaStream_t st);   // n_fft 256
+                   int device, cudaStream_t st);
+// tau > 0 fused into the part-warp pair kernels (tu_psmooth.cu); XsGeom: kernel_w32x2s.cuh.  -1: no instantiation for the hop
+int launch_pair_s_l4(int out_kind, const FrameGeom& g, const XsGeom& x, const PairPlan& p, const Epilogue& ep, void* out,
+                     int grid, int device, cudaStream_t st);
+int launch_pair_s_l3(int out_kind, const FrameGeom& g, const XsGeom& x, const PairPlan& p, const Epilogue& ep, void* out,
+                     int grid, int device, cudaStream_t st);
+int launch_pair_s_l2(int out_kind, const FrameGeom& g, const XsGeom& x, const PairPlan& p, const Epilogue& ep, void* out,
+                     int grid, int device, cudaStream_t st);   // n_fft 256
 inline bool pair_kernel_serves(int n_fft, int hop) {
   const int l = n_fft == 1024 ? 16 : n_fft == 512 ? 8 : n_fft == 256 ? 4 : 0;
   if (!l || hop % (2 * l)) return false;

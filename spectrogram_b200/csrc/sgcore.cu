@@ -524,19 +524,25 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
                            bool* done) {
   *done = false;
   const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
-  if (pl.n_fft != sg::kW32N || (cfg.hop != 512 && cfg.hop != 256) || (e->kernel_variant != 0 && e->kernel_variant != 7)) return SG_OK;
+  // n_fft 2048: kernel_w32x2s.cuh; n_fft 1024 / 512 / 256: kernel_pair_s.cuh (chained segments only); hop n_fft/4 or n_fft/8
+  const bool part_warp = pl.n_fft == 1024 || pl.n_fft == 512 || pl.n_fft == 256;
+  if ((pl.n_fft != sg::kW32N && !part_warp) || (cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft) ||
+      (e->kernel_variant != 0 && e->kernel_variant != 7))
+    return SG_OK;
+  const int bins = pl.n_fft / 2;
+  const int step_frames = part_warp ? 2 * (32 / (pl.n_fft / 64)) : 2;   // frames a warp takes at once
   // Every clip is one chain of segments, so the kernel keeps min(n_clips, SMs) CTAs busy.  Below ~2/3 of the SMs the
   // two-kernel path wins (64 x 60 s clips: 1.57 ms against 3.86 ms here, two clips 0.078 against 0.172 ms); variant 7
   // forces this kernel for any clip count (the tests use it to reach the look-back mode).
   if (e->kernel_variant != 7 && 3 * n_clips < 2 * (long long)e->sm_count) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
-  const int grid_max = e->sm_count, nw = 12;
+  const int grid_max = e->sm_count, nw = part_warp ? 8 * (step_frames / 2) : 12;   // pairs in one round of a CTA's warps
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
-  auto even_up = [](long long v) { return (v + 1) & ~1LL; };
+  auto even_up = [step_frames](long long v) { return (v + step_frames - 1) / step_frames * step_frames; };   // whole warp steps
   long long segs, seg_frames;
-  if (2 * n_clips <= grid_max) {
+  if (2 * n_clips <= grid_max && !part_warp) {
     // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
     seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
     x.mode = 1;
@@ -564,14 +570,14 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   x.dec = (float)std::pow((double)cfg.smoothing, (double)seg_frames);
   x.state_in = state;
   x.state_out = state;
-  const size_t state_bytes = (size_t)n_clips * sg::kW32M * sizeof(float);
+  const size_t state_bytes = (size_t)n_clips * bins * sizeof(float);
   if (x.mode == 1) {
     // the segments of a clip run concurrently and every one of them reads the clip's initial state: the final state
     // goes to a buffer of its own and is copied over afterwards
     SG_TRY(e->xs_state.reserve(state_bytes));
     x.state_out = (float*)e->xs_state.p;
   }
-  SG_TRY(e->xs_carry.reserve((size_t)tasks * 512 * sizeof(float2)));
+  SG_TRY(e->xs_carry.reserve((size_t)tasks * (bins / 2) * sizeof(float2)));
   if ((size_t)tasks * sizeof(unsigned) > e->xs_flags.cap) {
     SG_TRY(e->xs_flags.reserve(std::max<size_t>(4 * (size_t)tasks, 4096) * sizeof(unsigned)));
     SG_CUDA(cudaMemsetAsync(e->xs_flags.p, 0, e->xs_flags.cap, st));   // flags only ever hold epochs of earlier launches
@@ -580,13 +586,22 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   x.flags = (unsigned*)e->xs_flags.p;
   x.epoch = ++e->xs_epoch;
   sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
-  const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
   const int grid = (int)std::min<long long>(tasks, grid_max);
-  SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
+  if (part_warp) {
+    const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
+    const int rc = pl.n_fft == 1024 ? sg::launch_pair_s_l4(cfg.output, g, x, pp, ep, out, grid, e->device, st)
+                   : pl.n_fft == 512 ? sg::launch_pair_s_l3(cfg.output, g, x, pp, ep, out, grid, e->device, st)
+                                     : sg::launch_pair_s_l2(cfg.output, g, x, pp, ep, out, grid, e->device, st);
+    SG_CUDA((cudaError_t)rc);
+    e->last_kernel = pl.n_fft == 1024 ? "p16s" : pl.n_fft == 512 ? "p8s" : "p4s";
+  } else {
+    const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
+    SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
+    e->last_kernel = "warp32x32x2s";
+  }
   if (x.mode == 1) SG_CUDA(cudaMemcpyAsync(state, x.state_out, state_bytes, cudaMemcpyDeviceToDevice, st));
   e->launches++;
-  e->last_kernel = "warp32x32x2s";
   *done = true;
   return SG_OK;
 }

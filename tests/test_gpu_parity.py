@@ -672,3 +672,94 @@ def test_fused_smoothing_kernel_on_frame_ranges_of_a_long_clip(engine):
     two = engine.spectrogram(x, opts)                                     # automatic: the two-kernel path
     assert engine.last_kernel != "warp32x32x2s"
     assert np.all(np.abs(two - got) <= 2e-5 * np.abs(got) + 1e-7 * got.max(axis=-1, keepdims=True))
+
+
+# ----------------------------------------------------------------------------- fused smoothing, n_fft 1024 / 512 / 256
+PS_KERNEL = {1024: "p16s", 512: "p8s", 256: "p4s"}
+
+
+@pytest.mark.parametrize("n_fft,hop_div,n_clips,frames,extra,align", [
+    (1024, 4, 3, 333, 77, O.ALIGN_ANALYSER),     # zero history, odd frame count, partial last step
+    (1024, 8, 2, 700, 0, O.ALIGN_VALID),         # hop n_fft / 8
+    (1024, 4, 160, 130, 0, O.ALIGN_VALID),       # more tasks than CTAs: several tasks per CTA
+    (512, 4, 5, 1001, 13, O.ALIGN_VALID),        # four pairs per warp; a clip cut into chained segments
+    (512, 8, 150, 90, 0, O.ALIGN_ANALYSER),
+    (256, 4, 2, 2500, 3, O.ALIGN_VALID),         # eight pairs per warp, long chains
+    (256, 8, 149, 61, 0, O.ALIGN_ANALYSER),      # clips shorter than one round of the CTA's warps
+])
+def test_fused_smoothing_part_warp_kernels_match_the_oracle(engine, n_fft, hop_div, n_clips, frames, extra, align):
+    hop = n_fft // hop_div
+    clip_len = n_fft + (frames - 1) * hop + extra
+    rng = np.random.default_rng(n_fft + n_clips)
+    x = (0.05 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    x += O.chirp(clip_len, 48000.0, 100.0, 15000.0, 0.3)[None, :]
+    sel = np.unique(np.r_[0, min(1, n_clips - 1), n_clips // 2, n_clips - 1])
+    cfg = O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, align=align, output=O.OUT_F32_MAG)
+    ref_mag = O.spectrogram(x[sel], cfg)
+    for out in ("mag", "db", "u8", "rgba"):
+        opts = sg.Options(fftSize=n_fft, hop=hop, output=out, smoothingTimeConstant=0.8, align=ALIGN[align])
+        engine.set_kernel_variant(7)
+        try:
+            got = engine.spectrogram(x, opts)
+        finally:
+            engine.set_kernel_variant(0)
+        assert engine.last_kernel == PS_KERNEL[n_fft]
+        if out == "mag":
+            assert_mag_close(got[sel], ref_mag)
+        elif out == "db":
+            assert_db_close(got[sel], ref_mag)
+        elif out == "u8":
+            got_u8 = got
+            assert_bytes_close(got[sel], O.finish(ref_mag, O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, align=align)))
+        else:
+            assert np.array_equal(got, O.colormap_lut()[got_u8])
+
+
+@pytest.mark.parametrize("n_fft", [1024, 512, 256])
+def test_fused_smoothing_part_warp_automatic_selection_and_paths_agree(engine, n_fft):
+    """From ~2/3 of the SMs in clips the fused kernel is the automatic choice; the two-kernel path (forced by a
+    device-resident batch below the threshold) agrees with it to rounding, and both with the oracle."""
+    import torch
+    rng = np.random.default_rng(n_fft)
+    hop = n_fft // 4
+    clip_len = n_fft + 499 * hop
+    x = torch.from_numpy((0.2 * rng.standard_normal((200, clip_len))).astype(np.float32)).cuda()
+    opts = sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=0.75)
+    frames = engine.num_frames(opts, clip_len)
+
+    def run(n):
+        out = torch.empty((n, frames, n_fft // 2), dtype=torch.float32, device="cuda")
+        engine.spectrogram_device(x.data_ptr(), n, clip_len, clip_len, opts, out.data_ptr())
+        engine.synchronize()
+        return out.cpu().numpy()
+
+    a = run(200)
+    assert engine.last_kernel == PS_KERNEL[n_fft]
+    b = run(3)
+    assert engine.last_kernel != PS_KERNEL[n_fft]
+    assert np.all(np.abs(b - a[:3]) <= 2e-5 * np.abs(a[:3]) + 1e-7 * a[:3].max(axis=-1, keepdims=True))
+    ref = O.spectrogram(x[:2].cpu().numpy(), O.Config(n_fft=n_fft, hop=hop, smoothing=0.75, output=O.OUT_F32_MAG))
+    assert_mag_close(a[:2], ref)
+
+
+@pytest.mark.parametrize("n_fft", [1024, 256])
+def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_fft):
+    rng = np.random.default_rng(8)
+    hop = n_fft // 4
+    clip_len = n_fft + 90 * hop
+    x = (0.2 * rng.standard_normal((2, clip_len))).astype(np.float32)
+    x[0, n_fft + 20 * hop + 5] = np.nan        # four frames of clip 0 see the NaN
+    x[1, n_fft + 33 * hop + 9] = np.inf
+    cfg = O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, output=O.OUT_F32_MAG)
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = O.spectrogram(x, cfg)
+    engine.set_kernel_variant(7)
+    try:
+        got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=0.8))
+    finally:
+        engine.set_kernel_variant(0)
+    assert engine.last_kernel == PS_KERNEL[n_fft]
+    for c in (0, 1):
+        bad = np.all(ref[c] == 0, axis=1)
+        assert bad.sum() == 4 and np.all(got[c][bad] == 0)
+    assert_mag_close(got, ref)
