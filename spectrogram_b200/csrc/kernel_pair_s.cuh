@@ -286,7 +286,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
         ek[i] = active ? (has_b ? fmaf(x.tau, pk[i].v.x, pk[i].v.y) : pk[i].v.x) : 0.f;
         em[i] = active ? (has_b ? fmaf(x.tau, pm[i].v.x, pm[i].v.y) : pm[i].v.x) : 0.f;
       });
-      static_for<0, 5 - LOG2L>([&](auto ss) {       // inclusive scan, reaching back 2^s groups
+      // inclusive scan, reaching back 2^s groups (two groups: the exclusive values below are the raw maps already)
+      static_for<0, (PW > 2 ? 5 - LOG2L : 0)>([&](auto ss) {
         constexpr int sx = decltype(ss)::value, o = 1 << sx;
         const bool take = h >= o;
         const float dm = take ? d : 0.f;            // groups without a partner keep their map
