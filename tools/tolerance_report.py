@@ -44,6 +44,9 @@ CASES = [
     ("2048/512 fused smoothing 0.8", 2048, 512, "blackman", 44100, 7, 0.8),
     ("2048/160 two-kernel smoothing 0.8", 2048, 160, "blackman", 44100, 0, 0.8),
     ("1024/256 pair L=16", 1024, 256, "blackman", 48000, 0, 0.0),
+    ("1024/256 fused smoothing 0.8", 1024, 256, "blackman", 48000, 7, 0.8),
+    ("512/128 fused smoothing 0.8", 512, 128, "blackman", 48000, 7, 0.8),
+    ("256/64 fused smoothing 0.8", 256, 64, "blackman", 48000, 7, 0.8),
     ("1024/128 pair L=16 (config 5)", 1024, 128, "blackman", 48000, 0, 0.0),
     ("512/160 pair L=8 (config 2)", 512, 160, "hann", 16000, 0, 0.0),
     ("512/100 16x16", 512, 100, "hann", 16000, 0, 0.0),
