@@ -4,16 +4,16 @@
   magnitude  |d| <= 1e-4*|ref| + 3.5e-7*frame_peak
              (a float32 FFT has an absolute error floor of ~2-3e-7 of the frame's largest bin; a
              purely relative bound cannot hold on bins ~140 dB below the peak)
-  dB         |d| <= 1e-3 dB on bins within 55 dB of the frame peak; elsewhere the bound the
+  dB         |d| <= 1e-3 dB on bins within 60 dB of the frame peak; elsewhere the bound the
              magnitude tolerance implies
   byte       |d| <= 1 LSB everywhere, at most 0.2 % of the bytes off by that one level
 The reference against which these are taken is the float64 oracle (oracle/analyser_oracle.py).
 
-How much of them the kernels use is measured by tools/tolerance_report.py (profiles/r02_tolerance_report.txt: 17
+How much of them the kernels use is measured by tools/tolerance_report.py (profiles/r02_tolerance_report.txt: 20
 kernel/shape cases x 4 signals).  Worst cases over every kernel family: |d|/peak 3.4e-7; the magnitude bound is 82 %
 used with a floor of 2e-7 and exceeded (1.64x) with SURVEY section 7's 1e-7, so the floor sits at 3.5e-7 (about 2x
-the need); dB error 1.8e-4 within 50 dB of the peak, 7.2e-4 within 60 dB, 2.9e-3 within 70 dB, 7.7e-3 within 80 dB,
-so 1e-3 dB cannot be promised at SURVEY's 80 dB with float32 arithmetic and the window sits at 55 dB; byte mismatch
+the need); dB error 2.1e-4 within 50 dB of the peak, 7.2e-4 within 60 dB, 2.9e-3 within 70 dB, 7.7e-3 within 80 dB,
+so 1e-3 dB cannot be promised at SURVEY's 80 dB with float32 arithmetic and the window sits at 60 dB; byte mismatch
 rate at most 6.5e-4, never more than one level.
 """
 import numpy as np
@@ -21,7 +21,7 @@ import numpy as np
 MAG_REL = 1e-4
 MAG_FLOOR = 3.5e-7
 DB_TOL = 1e-3
-DB_WINDOW = 55.0
+DB_WINDOW = 60.0
 
 
 def assert_mag_close(got, ref_mag):
