@@ -686,6 +686,9 @@ PS_KERNEL = {1024: "p16s", 512: "p8s", 256: "p4s"}
     (512, 8, 150, 90, 0, O.ALIGN_ANALYSER),
     (256, 4, 2, 2500, 3, O.ALIGN_VALID),         # eight pairs per warp, long chains
     (256, 8, 149, 61, 0, O.ALIGN_ANALYSER),      # clips shorter than one round of the CTA's warps
+    (512, 4, 3, 1, 0, O.ALIGN_VALID),            # a single frame per clip: one lone frame A, every other lane group idle
+    (1024, 4, 2, 2, 0, O.ALIGN_VALID),           # exactly one pair
+    (256, 4, 2, 5, 7, O.ALIGN_ANALYSER),         # fewer frames than one step holds
 ])
 def test_fused_smoothing_part_warp_kernels_match_the_oracle(engine, n_fft, hop_div, n_clips, frames, extra, align):
     hop = n_fft // hop_div
