@@ -141,6 +141,10 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + L * m); });
   }
 
+#ifdef SG_DEBUG
+  unsigned dbg_q = warp;                        // this step's place in the CTA's step sequence (round robin over warps)
+  unsigned* dbg_tags = dbg_cta_tags();          // one tag per state slot (i, t): the step that wrote it, plus one
+#endif
   while (true) {
     const PsItem cur = ps_item(x, fpc, it);
     const int p = u * PW + h;
@@ -317,7 +321,15 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
         while (ld_acquire_u32(x.flags + (long long)(cur.seg - 1) * x.n_clips + cur.clip) != x.epoch) {}
       __syncwarp();
     }
+#ifdef SG_DEBUG
+    if (!g_sg_dbg.break_chain)
+#endif
     while (!mbar_try_wait(s_bar + warp, turn)) {}
+#ifdef SG_DEBUG
+    if (lane == 0) dbg_count_iteration();
+    // every slot must hold the state the step just before this one left
+    if (dbg_q != 0) static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_check(dbg_tags, i * L + t, dbg_q, 3); });
+#endif
     if (u == 0) {
       // first step of a work item: the state the segment starts from
       if (h == 0) {
@@ -368,6 +380,11 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
         __syncwarp();
       }
     }
+#ifdef SG_DEBUG
+    if (h == PW - 1) static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_write(dbg_tags, i * L + t, dbg_q + 1); });
+    __threadfence_block();
+    dbg_q += NW;
+#endif
     __syncwarp();
     if (lane == 0) mbar_arrive(s_bar + (warp + 1 == NW ? 0 : warp + 1));
     turn ^= 1;

@@ -119,6 +119,9 @@ int launch_pcm_ingest(int format, const PcmGeom& g, long long n_clips, const Pcm
 #ifdef SG_DEBUG
 int dbg_attach_w32x2p(const DbgState& st);
 int dbg_attach_w32x2s(const DbgState& st);
+int dbg_attach_psmooth_l2(const DbgState& st);
+int dbg_attach_psmooth_l3(const DbgState& st);
+int dbg_attach_psmooth_l4(const DbgState& st);
 #endif
 
 constexpr int kMaxDevices = 64;

@@ -759,6 +759,9 @@ int sg_engine_create(int device, sg_engine** out) {
       e->dbg.break_chain = brk && brk[0] == '1';
       SG_CUDA((cudaError_t)sg::dbg_attach_w32x2p(e->dbg));
       SG_CUDA((cudaError_t)sg::dbg_attach_w32x2s(e->dbg));
+      SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l2(e->dbg));
+      SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l3(e->dbg));
+      SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l4(e->dbg));
     }
 #endif
     return SG_OK;
@@ -1033,7 +1036,8 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
 
 #ifdef SG_DEBUG
 // debug build only (not part of include/sgcore.h): mismatches per check site -- 0 exchange planes of the frame-pair
-// kernel, 1 its byte stage, 2 the state hand-off of the fused smoothing kernel -- and, in the last entry, how many
+// kernel, 1 its byte stage, 2 the state hand-off of the fused smoothing kernel (n_fft 2048), 3 the same of the part-warp
+// kernels (n_fft 1024 / 512 / 256) -- and, in the last entry, how many
 // warp iterations ran with the checks armed
 extern "C" int sg_debug_counts(sg_engine* e, unsigned long long out[16]) {
   if (!e || !out) return fail(SG_ERR_INVALID_ARG, "null argument");

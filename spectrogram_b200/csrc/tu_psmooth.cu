@@ -42,4 +42,8 @@ int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, con
   });
 }
 
+#ifdef SG_DEBUG
+int SG_CAT(dbg_attach_psmooth_l, SG_PAIR_LOG2L)(const DbgState& st) { return (int)dbg_attach(st); }
+#endif
+
 }  // namespace sg
