@@ -524,9 +524,9 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
                            bool* done) {
   *done = false;
   const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
-  // n_fft 2048: kernel_w32x2s.cuh; n_fft 1024 / 512 / 256: kernel_pair_s.cuh (chained segments only); hop n_fft/4 or n_fft/8
+  // n_fft 2048: kernel_w32x2s.cuh; n_fft 1024 / 512 / 256: kernel_pair_s.cuh (chained segments only); hop n_fft/2, /4 or /8
   const bool part_warp = pl.n_fft == 1024 || pl.n_fft == 512 || pl.n_fft == 256;
-  if ((pl.n_fft != sg::kW32N && !part_warp) || (cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft) ||
+  if ((pl.n_fft != sg::kW32N && !part_warp) || (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft) ||
       (e->kernel_variant != 0 && e->kernel_variant != 7))
     return SG_OK;
   const int bins = pl.n_fft / 2;

@@ -1,5 +1,5 @@
 // Translation unit: part-warp frame-pair kernels with the smoothing recurrence fused in (n_fft 1024 | 512 | 256, hop
-// n_fft/4 or n_fft/8, tau > 0), compiled once per lane-group size (-DSG_PAIR_LOG2L=4|3|2).
+// n_fft/2, n_fft/4 or n_fft/8, tau > 0), compiled once per lane-group size (-DSG_PAIR_LOG2L=4|3|2).
 #include "kernel_pair_s.cuh"
 
 #ifndef SG_PAIR_LOG2L
@@ -37,6 +37,7 @@ int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, con
     switch (hopj) {
       case 4: return launch_ps<OUT, 4>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 8
       case 8: return launch_ps<OUT, 8>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 4
+      case 16: return launch_ps<OUT, 16>(g, x, p, ep, out, grid, device, st);   // hop = n_fft / 2
       default: return -1;
     }
   });

@@ -1,4 +1,4 @@
-// Translation unit: frame-pair kernel with the smoothing recurrence fused in (n_fft 2048, hop 512 / 256, tau > 0).
+// Translation unit: frame-pair kernel with the smoothing recurrence fused in (n_fft 2048, hop 1024 / 512 / 256, tau > 0).
 #include <cstdlib>
 
 #include "kernel_w32x2s.cuh"
@@ -29,6 +29,7 @@ int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Pl
     //  and three warps per scheduler waiting on one ring; four chains over slot groups 433 M; loads inside the
     //  untangle 409 M; without waiting at all, wrong results, 518 M: the ordering itself costs 9 %)
     if (g.hop == 256) return launch_xs<OUT, 4, 8, true, 1>(g, x, p, ep, out, grid, device, st);
+    if (g.hop == 1024) return launch_xs<OUT, 16, 8, true, 1>(g, x, p, ep, out, grid, device, st);
     return launch_xs<OUT, 8, 8, true, 1>(g, x, p, ep, out, grid, device, st);
   });
 }

@@ -566,6 +566,8 @@ def test_time_parallel_scan_agrees_with_the_sequential_recurrence(engine):
     (2, 2048 + 700 * 256, 256, O.ALIGN_VALID),        # hop 256 instantiation
     (160, 2048 + 120 * 512, 512, O.ALIGN_VALID),      # more clips than half the SMs: chained segments
     (301, 2048 + 97 * 512, 512, O.ALIGN_ANALYSER),    # chained, odd frames per clip, several tasks per CTA
+    (150, 2048 + 75 * 1024 + 5, 1024, O.ALIGN_ANALYSER),  # hop n/2 instantiation, chained
+    (2, 2048 + 400 * 1024, 1024, O.ALIGN_VALID),      # hop n/2, look-back mode
 ])
 def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, hop, align):
     rng = np.random.default_rng(n_clips)
@@ -686,6 +688,8 @@ PS_KERNEL = {1024: "p16s", 512: "p8s", 256: "p4s"}
     (512, 8, 150, 90, 0, O.ALIGN_ANALYSER),
     (256, 4, 2, 2500, 3, O.ALIGN_VALID),         # eight pairs per warp, long chains
     (256, 8, 149, 61, 0, O.ALIGN_ANALYSER),      # clips shorter than one round of the CTA's warps
+    (1024, 2, 4, 500, 9, O.ALIGN_ANALYSER),      # hop n_fft / 2
+    (256, 2, 151, 77, 0, O.ALIGN_VALID),
     (512, 4, 3, 1, 0, O.ALIGN_VALID),            # a single frame per clip: one lone frame A, every other lane group idle
     (1024, 4, 2, 2, 0, O.ALIGN_VALID),           # exactly one pair
     (256, 4, 2, 5, 7, O.ALIGN_ANALYSER),         # fewer frames than one step holds
