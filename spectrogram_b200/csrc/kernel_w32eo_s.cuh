@@ -1,0 +1,368 @@
+// n_fft = 4096 with smoothingTimeConstant > 0 in ONE pass: the even/odd kernel of kernel_w32eo.cuh (one frame per warp,
+// the two 1024-point sub-transforms in the halves of the packed registers) with the AnalyserNode recurrence
+// X^_t[k] = tau X^_{t-1}[k] + (1 - tau) |X_t[k]|  (3D/visualizer.js:351,357,362; [SPEC] step 4) fused between the untangle
+// and the dB / byte epilogue, organised like the chain mode of kernel_w32x2s.cuh: a CTA owns a SEGMENT of consecutive
+// frames of one clip, its 8 warps take the frames round robin and run window -> FFT -> combine -> untangle -> sqrt
+// concurrently, and only the state update -- 16 x (LDS.128, 4 FMA, STS.128) per lane -- goes from warp to warp in frame
+// order through an mbarrier chain.  X^ of the segment: 8 KB of shared memory, slot (i, lane) = the four bins
+// (k', k' + 1024, 2048 - k', 1024 - k') of k' = lane + 32 i, exactly the four powers a lane's untangle step yields.
+// Segments of a clip are chained through a carry vector and a flag in global memory (tasks dealt segment-major,
+// cooperative launch).  One frame per turn: the chained form is the sequential arithmetic bit for bit.
+// [SPEC] "non-finite X^ -> 0": one integer max over the lane's powers per frame and a warp vote pick the per-value path.
+#pragma once
+#include "kernel_w32eo.cuh"
+#include "kernel_w32x2s.cuh"   // XsGeom, acquire/release, mbarrier helpers
+
+namespace sg {
+
+constexpr int kEsWarps = 8;
+constexpr int kEsStateBytes = 16 * 32 * 16;
+constexpr int kEsSmemBytes = kEoTableBytes + kEsStateBytes + kEsWarps * 8 + kEsWarps * kXpPlaneBytes;
+
+struct EsItem {
+  int it, clip, seg, f0, nfr;
+  bool valid;
+};
+__device__ __forceinline__ EsItem es_item(const XsGeom& x, int fpc, int it) {
+  EsItem c;
+  c.it = it;
+  const unsigned n_clips = (unsigned)x.n_clips, n_tasks = (unsigned)x.segs * n_clips;   // < 2^31 (host checks)
+  const unsigned task = blockIdx.x + (unsigned)it * gridDim.x;
+  c.valid = task < n_tasks;
+  c.seg = (int)(task / n_clips);
+  c.clip = (int)(task - (unsigned)c.seg * n_clips);
+  c.f0 = c.seg * x.seg_frames;
+  c.nfr = min(x.seg_frames, fpc - c.f0);
+  return c;
+}
+
+// natural bins of state slot (i, lane): (k', k' + 1024, 2048 - k', 1024 - k'); lane 0's slot 0 carries bins 1536 and 512
+// in its mirror halves (the mirrors of k' = 0 are the dropped Nyquist bin and bin 1024 again)
+__device__ __forceinline__ void es_bins(int i, int lane, int (&b)[4]) {
+  const int k = lane + 32 * i;
+  const int mk = (i == 0 && lane == 0) ? 512 : 1024 - k;
+  b[0] = k; b[1] = k + 1024; b[2] = 1024 + mk; b[3] = mk;
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(kEsWarps * 32, 1)
+stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
+  using T = typename OutElem<OUT>::type;
+  constexpr int NW = kEsWarps;
+  extern __shared__ float4 smem_raw[];
+  float4* s_win4 = smem_raw;                                           // [1024] (w[4m] .. w[4m+3])
+  float2* s_twb = reinterpret_cast<float2*>(s_win4 + 1024);            // [5][32]  W_{32*2^u}^lane
+  float2* s_ut = s_twb + 5 * 32;                                       // [16][32] W_4096^{lane + 32 i}
+  float4* s_state = reinterpret_cast<float4*>(s_ut + 16 * 32);         // [16][32] X^ of the four bins of a slot
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_state + 16 * 32);    // [NW] the turn of warp w
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(s_bar + NW) + warp * kXpPlaneBytes;
+  float4* xp = reinterpret_cast<float4*>(wbase);                       // exchange planes
+  uint16_t* sb16 = reinterpret_cast<uint16_t*>(wbase);                 // byte stage, aliases the planes
+
+  {
+    const float4* w4 = reinterpret_cast<const float4*>(pl.win);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_win4[i] = __ldg(w4 + i);
+    for (int i = threadIdx.x; i < 5 * 32; i += blockDim.x) s_twb[i] = __ldg(pl.tw2 + ((1 << (i >> 5)) - 1) * 32 + (i & 31));
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) s_ut[i] = __ldg(pl.tab + 32 + i);
+    if (threadIdx.x < NW) mbar_init(s_bar + threadIdx.x, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_arrive(s_bar);      // warp 0 holds the first turn
+  unsigned turn = 0;
+
+  const int fpc = (int)g.frames_per_clip;
+  const int partner = (32 - lane) & 31;
+  const bool lane0 = lane == 0;
+  const bool base_aligned = (reinterpret_cast<uintptr_t>(g.pcm) & 15) == 0;
+  // frame p of item c: offset of its first sample from g.pcm, and whether the 16-byte loader can express it
+  auto frame_off = [&](const EsItem& c, int p) { return c.clip * g.clip_stride + g.start0 + (long long)(c.f0 + p) * g.hop; };
+  auto frame_fast = [&](const EsItem& c, int p, long long off) {
+    const long long start = g.start0 + (long long)(c.f0 + p) * g.hop;
+    return c.valid && start >= 0 && start + kEoN <= g.clip_len && base_aligned && (off & 3) == 0;
+  };
+  auto advance = [&](EsItem& c, int& p) {
+    p += NW;
+    while (c.valid && p >= c.nfr) {
+      p -= c.nfr;
+      c = es_item(x, fpc, c.it + 1);
+    }
+  };
+
+  int it, p = warp - NW;
+  bool cur_fast;
+  float4 s[32];
+  const float4* idle_src = reinterpret_cast<const float4*>(pl.win) + lane;   // 4096 readable floats
+  auto elem_of = [](int m) { return (m >> 1) + 16 * (m & 1); };              // m = 2j -> j, 2j + 1 -> j + 16
+  {
+    EsItem c0 = es_item(x, fpc, 0);
+    advance(c0, p);
+    if (!c0.valid) return;
+    it = c0.it;
+    const long long off = frame_off(c0, p);
+    cur_fast = frame_fast(c0, p, off);
+    const float4* src = cur_fast ? reinterpret_cast<const float4*>(g.pcm + off) + lane : idle_src;
+    static_for<0, 32>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f4(src + 32 * elem_of(m)); });
+  }
+
+#ifdef SG_DEBUG
+  unsigned dbg_q = warp;                        // this frame's place in the CTA's frame sequence (round robin over warps)
+  unsigned* dbg_tags = dbg_cta_tags();          // one tag per state slot (i, lane): the frame that wrote it, plus one
+#endif
+  while (true) {
+    const EsItem cur = es_item(x, fpc, it);
+    const int tf = cur.f0 + p;                    // frame index inside the clip
+    // ---- steps 1-2 (+ FFT stage 1): window, even/odd complex samples into the register halves, bit-reversed
+    C2 a[32];
+    if (cur_fast) {
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
+        window_stage1_eo(a[r0], a[r1], s[2 * j], s[2 * j + 1], s_win4[lane + 32 * j], s_win4[lane + 32 * (j + 16)]);
+      });
+    } else {
+      const long long start = g.start0 + (long long)tf * g.hop;
+      const float* __restrict__ xc = g.pcm + cur.clip * g.clip_stride;
+      auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xc + q) : 0.f; };
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+        const long long o0 = start + 4 * (lane + 32 * j), o1 = start + 4 * (lane + 32 * (j + 16));
+        window_stage1_eo(a[r0], a[r1], make_float4(ld(o0), ld(o0 + 1), ld(o0 + 2), ld(o0 + 3)),
+                         make_float4(ld(o1), ld(o1 + 1), ld(o1 + 2), ld(o1 + 3)), s_win4[lane + 32 * j],
+                         s_win4[lane + 32 * (j + 16)]);
+      });
+    }
+
+    // ---- pass 1, exchange, pass 2: kernel_w32eo.cuh
+    dit2_stage_const<2>(a);
+    dit2_stage_const<3>(a);
+    dit2_stage_const<4>(a);
+    dit2_stage_const<5>(a);
+    {
+      float2* wre = reinterpret_cast<float2*>(xp) + ((lane >> 1) * kXpStride) * 2 + (lane & 1);
+      float2* wim = wre + 16 * kXpStride * 2;
+      static_for<0, 32>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        wre[2 * q] = a[q].re.v;
+        wim[2 * q] = a[q].im.v;
+      });
+      asm volatile("bar.sync %0, 32;" ::"r"(warp + 1) : "memory");
+      const float4* rre = xp + lane;
+      const float4* rim = rre + 16 * kXpStride;
+      static_for<0, 16>([&](auto qq) {
+        constexpr int q0 = decltype(qq)::value;
+        constexpr int j = bitrev(q0, 4);
+        const float4 vr = rre[j * kXpStride], vi = rim[j * kXpStride];
+        a[q0].re = P2(vr.x, vr.y); a[q0 + 16].re = P2(vr.z, vr.w);
+        a[q0].im = P2(vi.x, vi.y); a[q0 + 16].im = P2(vi.z, vi.w);
+      });
+      __syncwarp();
+    }
+    dit2_stage_gen<1>(a, s_twb[0 * 32 + lane]);
+    dit2_stage_gen<2>(a, s_twb[1 * 32 + lane]);
+    dit2_stage_gen<3>(a, s_twb[2 * 32 + lane]);
+    dit2_stage_gen<4>(a, s_twb[3 * 32 + lane]);
+    dit2_stage_gen<5>(a, s_twb[4 * 32 + lane]);
+    // now a[i] = (E[k'], O[k']), k' = lane + 32 i
+
+    // ---- next frame of this warp
+    int nit, np = p;
+    bool has_next, nxt_fast;
+    const float4* nsrc;
+    {
+      EsItem nxt = cur;
+      advance(nxt, np);
+      nit = nxt.it;
+      has_next = nxt.valid;
+      const long long noff = frame_off(nxt, np);
+      nxt_fast = has_next && frame_fast(nxt, np, noff);
+      nsrc = nxt_fast ? reinterpret_cast<const float4*>(g.pcm + noff) + lane : idle_src;
+    }
+
+    // ---- combine + untangle (kernel_w32eo.cuh), then (1 - tau) |X| / N of the four bins of every slot
+    auto combine = [&](const C2& z, float wx, float wy, bool swap) {   // (E, O) -> (E + wO, E - wO), or swapped
+      const float er = z.re.v.x, ei = z.im.v.x, orr = z.re.v.y, oi = z.im.v.y;
+      const float pr = fmaf(orr, wx, fmaf(oi, -wy, er));
+      const float pi = fmaf(oi, wx, fmaf(orr, wy, ei));
+      const float mr = fmaf(er, 2.f, -pr), mi = fmaf(ei, 2.f, -pi);
+      C2 r;
+      r.re = swap ? P2(mr, pr) : P2(pr, mr);
+      r.im = swap ? P2(mi, pi) : P2(pi, mi);
+      return r;
+    };
+    P2 p512;
+    {
+      P2 unused;   // W_2048^512 = -i; W_4096^512 = exp(-i pi/4)
+      untangle_eo(combine(a[16], 0.f, -1.f, false), combine(a[16], 0.f, -1.f, true),
+                  make_float2(0.70710678118654752440f, -0.70710678118654752440f), p512, unused);
+    }
+    static_for<0, 16>([&](auto ii) {
+      constexpr int i = 15 - decltype(ii)::value;
+      constexpr int src = 31 - i, own = (32 - i) & 31;
+      const float mra = __shfl_sync(0xffffffffu, a[src].re.v.x, partner);
+      const float mrb = __shfl_sync(0xffffffffu, a[src].re.v.y, partner);
+      const float mia = __shfl_sync(0xffffffffu, a[src].im.v.x, partner);
+      const float mib = __shfl_sync(0xffffffffu, a[src].im.v.y, partner);
+      a[src].re = P2(lane0 ? a[own].re.v.x : mra, lane0 ? a[own].re.v.y : mrb);
+      a[src].im = P2(lane0 ? a[own].im.v.x : mia, lane0 ? a[own].im.v.y : mib);
+    });
+    P2 pk[16], pm[16];   // pk[i]: bins (k', k' + 1024);  pm[i]: bins (2048 - k', 1024 - k')
+    unsigned worst = 0;
+    static_for<0, 16>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      const float2 u = s_ut[i * 32 + lane];                                  // W_4096^k'
+      const float wx = fmaf(u.x, u.x, -u.y * u.y), wy = (u.x + u.x) * u.y;    // W_2048^k' = its square
+      P2 qk, qm;
+      untangle_eo(combine(a[i], wx, wy, false), combine(a[31 - i], -wx, wy, true), u, qk, qm);
+      if constexpr (i == 0) qm = P2(lane0 ? p512.v.y : qm.v.x, lane0 ? p512.v.x : qm.v.y);
+      worst = max(max(worst, max(__float_as_uint(qk.v.x), __float_as_uint(qk.v.y))),
+                  max(__float_as_uint(qm.v.x), __float_as_uint(qm.v.y)));
+      pk[i] = mul2(P2(sqrt_ftz(qk.v.x), sqrt_ftz(qk.v.y)), bc(x.mscale));
+      pm[i] = mul2(P2(sqrt_ftz(qm.v.x), sqrt_ftz(qm.v.y)), bc(x.mscale));
+    });
+    const bool dirty = __any_sync(0xffffffffu, worst >= 0x7f800000u);
+
+    // ---- the recurrence, in frame order
+    if (p == 0 && cur.seg > 0) {
+      if (lane0)
+        while (ld_acquire_u32(x.flags + (long long)(cur.seg - 1) * x.n_clips + cur.clip) != x.epoch) {}
+      __syncwarp();
+    }
+#ifdef SG_DEBUG
+    if (!g_sg_dbg.break_chain)
+#endif
+    while (!mbar_try_wait(s_bar + warp, turn)) {}
+#ifdef SG_DEBUG
+    if (lane == 0) dbg_count_iteration();
+    if (dbg_q != 0) static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_check(dbg_tags, i * 32 + lane, dbg_q, 4); });
+#endif
+    if (p == 0) {
+      // first frame of a work item: the state the segment starts from
+      if (cur.seg == 0) {
+        const float* __restrict__ si = x.state_in ? x.state_in + (long long)cur.clip * kEoBins : nullptr;
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          int b[4];
+          es_bins(i, lane, b);
+          s_state[i * 32 + lane] = si ? make_float4(si[b[0]], si[b[1]], si[b[2]], si[b[3]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        });
+      } else {
+        const float4* __restrict__ cv =
+            reinterpret_cast<const float4*>(x.carry) + ((long long)(cur.seg - 1) * x.n_clips + cur.clip) * 512 + lane;
+        static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; s_state[i * 32 + lane] = __ldcg(cv + i * 32); });
+      }
+      __syncwarp();
+    }
+    if (!dirty) {
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const float4 st = s_state[i * 32 + lane];
+        pk[i] = P2(fmaf(x.tau, st.x, pk[i].v.x), fmaf(x.tau, st.y, pk[i].v.y));
+        pm[i] = P2(fmaf(x.tau, st.z, pm[i].v.x), fmaf(x.tau, st.w, pm[i].v.y));
+        s_state[i * 32 + lane] = make_float4(pk[i].v.x, pk[i].v.y, pm[i].v.x, pm[i].v.y);
+      });
+    } else {
+      static_for<0, 16>([&](auto ii) {   // [SPEC] a non-finite X^ is set to 0
+        constexpr int i = decltype(ii)::value;
+        const float4 st = s_state[i * 32 + lane];
+        pk[i] = P2(finite_or_zero(fmaf(x.tau, st.x, pk[i].v.x)), finite_or_zero(fmaf(x.tau, st.y, pk[i].v.y)));
+        pm[i] = P2(finite_or_zero(fmaf(x.tau, st.z, pm[i].v.x)), finite_or_zero(fmaf(x.tau, st.w, pm[i].v.y)));
+        s_state[i * 32 + lane] = make_float4(pk[i].v.x, pk[i].v.y, pm[i].v.x, pm[i].v.y);
+      });
+    }
+#ifdef SG_DEBUG
+    static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; dbg_write(dbg_tags, i * 32 + lane, dbg_q + 1); });
+    __threadfence_block();
+    dbg_q += NW;
+#endif
+    __syncwarp();
+    if (lane0) mbar_arrive(s_bar + (warp + 1 == NW ? 0 : warp + 1));
+    turn ^= 1;
+
+    if (p == cur.nfr - 1) {
+      // last frame of a work item: hand the state to the next segment (or to the caller)
+      if (cur.seg + 1 < x.segs) {
+        const long long me = (long long)cur.seg * x.n_clips + cur.clip;
+        float4* __restrict__ cv = reinterpret_cast<float4*>(x.carry) + me * 512 + lane;
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          cv[i * 32] = make_float4(pk[i].v.x, pk[i].v.y, pm[i].v.x, pm[i].v.y);
+        });
+        __threadfence();
+        __syncwarp();
+        if (lane0) st_release_u32(x.flags + me, x.epoch);
+      } else if (x.state_out != nullptr) {
+        float* __restrict__ so = x.state_out + (long long)cur.clip * kEoBins;
+        static_for<0, 16>([&](auto ii) {
+          constexpr int i = decltype(ii)::value;
+          int b[4];
+          es_bins(i, lane, b);
+          so[b[0]] = pk[i].v.x; so[b[1]] = pk[i].v.y; so[b[2]] = pm[i].v.x; so[b[3]] = pm[i].v.y;
+        });
+      }
+    }
+
+    // ---- epilogue: X^ -> dB / byte / colour; the next frame's loads ride in its 16 steps (two per step)
+    T* __restrict__ row_lo = out + ((long long)cur.clip * x.out_clip_rows + tf) * (long long)kEoBins;
+    T* __restrict__ row_hi = row_lo + 1024;
+    if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
+      const P2 scale = bc(2.f * ep.byte_a);
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int k = lane + 32 * i;
+        int mk = 1024 - k;
+        if constexpr (i == 0) { if (lane0) mk = 512; }
+        const P2 vk = fma2(P2(lg2_ftz(pk[i].v.x), lg2_ftz(pk[i].v.y)), scale, bc(ep.byte_b0));
+        const P2 vm = fma2(P2(lg2_ftz(pm[i].v.x), lg2_ftz(pm[i].v.y)), scale, bc(ep.byte_b0));
+        const unsigned k_lo = byte_of_scaled(vk.v.x), k_hi = byte_of_scaled(vk.v.y);
+        const unsigned m_hi = byte_of_scaled(vm.v.x), m_lo = byte_of_scaled(vm.v.y);
+        if constexpr (OUT == kOutU8) {
+          sb16[k] = (uint16_t)__byte_perm(k_lo, k_hi, 0x0040);
+          sb16[mk] = (uint16_t)__byte_perm(m_lo, m_hi, 0x0040);
+        } else {
+          row_lo[k] = __ldg(ep.lut + k_lo); row_lo[mk] = __ldg(ep.lut + m_lo);
+          row_hi[k] = __ldg(ep.lut + k_hi); row_hi[mk] = __ldg(ep.lut + m_hi);
+        }
+        s[2 * i] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i));
+        s[2 * i + 1] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i + 1));
+      });
+      if constexpr (OUT == kOutU8) {
+        __syncwarp();
+        // de-interleave the (lower, upper) byte pairs: 8 bins per lane per round, 8-byte coalesced stores
+        const uint4* s16 = reinterpret_cast<const uint4*>(sb16);
+        uint2* ra = reinterpret_cast<uint2*>(row_lo);
+        uint2* rb = reinterpret_cast<uint2*>(row_hi);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = s16[c * 32 + lane];
+          ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+          rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+        }
+      }
+    } else {
+      static_for<0, 16>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int k = lane + 32 * i;
+        int mk = 1024 - k;
+        if constexpr (i == 0) { if (lane0) mk = 512; }
+        P2 vk = pk[i], vm = pm[i];
+        if constexpr (OUT == kOutF32Db) {
+          vk = mul2(P2(lg2_ftz(vk.v.x), lg2_ftz(vk.v.y)), bc(2.f * ep.db_scale));
+          vm = mul2(P2(lg2_ftz(vm.v.x), lg2_ftz(vm.v.y)), bc(2.f * ep.db_scale));
+        }
+        row_lo[k] = vk.v.x; row_hi[k] = vk.v.y;
+        row_hi[mk] = vm.v.x; row_lo[mk] = vm.v.y;
+        s[2 * i] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i));
+        s[2 * i + 1] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i + 1));
+      });
+    }
+    __syncwarp();
+    if (!has_next) break;
+    it = nit;
+    p = np;
+    cur_fast = nxt_fast;
+  }
+}
+
+}  // namespace sg

@@ -109,6 +109,9 @@ struct EoPlan {
 };
 int launch_w32eo(int out_kind, int warps, const FrameGeom& g, const EoPlan& p, const Epilogue& ep, void* out, int sm_count,
                  int device, cudaStream_t st);
+// tau > 0 fused into the n_fft 4096 kernel (tu_w32eo_s.cu); XsGeom: kernel_w32x2s.cuh
+int launch_w32eo_s(int out_kind, const FrameGeom& g, const XsGeom& x, const EoPlan& p, const Epilogue& ep, void* out, int grid,
+                   int device, cudaStream_t st);
 
 // tu_pcm.cu: PCM ingestion (kernel_pcm.cuh)
 struct PcmGeom;
@@ -119,6 +122,7 @@ int launch_pcm_ingest(int format, const PcmGeom& g, long long n_clips, const Pcm
 #ifdef SG_DEBUG
 int dbg_attach_w32x2p(const DbgState& st);
 int dbg_attach_w32x2s(const DbgState& st);
+int dbg_attach_w32eo_s(const DbgState& st);
 int dbg_attach_psmooth_l2(const DbgState& st);
 int dbg_attach_psmooth_l3(const DbgState& st);
 int dbg_attach_psmooth_l4(const DbgState& st);

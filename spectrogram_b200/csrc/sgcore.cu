@@ -524,25 +524,31 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
                            bool* done) {
   *done = false;
   const bool bytes_out = cfg.output == SG_OUT_U8 || cfg.output == SG_OUT_RGBA8;
-  // n_fft 2048: kernel_w32x2s.cuh; n_fft 1024 / 512 / 256: kernel_pair_s.cuh (chained segments only); hop n_fft/2, /4 or /8
+  // n_fft 2048: kernel_w32x2s.cuh; n_fft 1024 / 512 / 256: kernel_pair_s.cuh (chained segments only); hop n_fft/2, /4 or /8.
+  // n_fft 4096: kernel_w32eo_s.cuh (chained segments only)
   const bool part_warp = pl.n_fft == 1024 || pl.n_fft == 512 || pl.n_fft == 256;
-  if ((pl.n_fft != sg::kW32N && !part_warp) || (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft) ||
-      (e->kernel_variant != 0 && e->kernel_variant != 7))
+  const bool even_odd = pl.n_fft == sg::kEoN;      // kernel_w32eo_s.cuh: any hop that keeps frames 16-byte aligned
+  if (e->kernel_variant != 0 && e->kernel_variant != 7) return SG_OK;
+  if (even_odd) {
+    if ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15)) return SG_OK;
+  } else if ((pl.n_fft != sg::kW32N && !part_warp) ||
+             (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft)) {
     return SG_OK;
+  }
   const int bins = pl.n_fft / 2;
-  const int step_frames = part_warp ? 2 * (32 / (pl.n_fft / 64)) : 2;   // frames a warp takes at once
+  const int step_frames = part_warp ? 2 * (32 / (pl.n_fft / 64)) : even_odd ? 1 : 2;   // frames a warp takes at once
   // Every clip is one chain of segments, so the kernel keeps min(n_clips, SMs) CTAs busy.  Below ~2/3 of the SMs the
   // two-kernel path wins (64 x 60 s clips: 1.57 ms against 3.86 ms here, two clips 0.078 against 0.172 ms); variant 7
   // forces this kernel for any clip count (the tests use it to reach the look-back mode).
   if (e->kernel_variant != 7 && 3 * n_clips < 2 * (long long)e->sm_count) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
-  const int grid_max = e->sm_count, nw = part_warp ? 8 * (step_frames / 2) : 12;   // pairs in one round of a CTA's warps
+  const int grid_max = e->sm_count, nw = part_warp ? 8 * (step_frames / 2) : even_odd ? 4 : 12;   // pairs in one round of a CTA's warps
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
   auto even_up = [step_frames](long long v) { return (v + step_frames - 1) / step_frames * step_frames; };   // whole warp steps
   long long segs, seg_frames;
-  if (2 * n_clips <= grid_max && !part_warp) {
+  if (2 * n_clips <= grid_max && !part_warp && !even_odd) {
     // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
     seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
     x.mode = 1;
@@ -588,7 +594,11 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
   const int grid = (int)std::min<long long>(tasks, grid_max);
-  if (part_warp) {
+  if (even_odd) {
+    const sg::EoPlan eo{pl.win, pl.w32_tw2, pl.eo_tab};
+    SG_CUDA((cudaError_t)sg::launch_w32eo_s(cfg.output, g, x, eo, ep, out, grid, e->device, st));
+    e->last_kernel = "eo4096s";
+  } else if (part_warp) {
     const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
     const int rc = pl.n_fft == 1024 ? sg::launch_pair_s_l4(cfg.output, g, x, pp, ep, out, grid, e->device, st)
                    : pl.n_fft == 512 ? sg::launch_pair_s_l3(cfg.output, g, x, pp, ep, out, grid, e->device, st)
@@ -759,6 +769,7 @@ int sg_engine_create(int device, sg_engine** out) {
       e->dbg.break_chain = brk && brk[0] == '1';
       SG_CUDA((cudaError_t)sg::dbg_attach_w32x2p(e->dbg));
       SG_CUDA((cudaError_t)sg::dbg_attach_w32x2s(e->dbg));
+      SG_CUDA((cudaError_t)sg::dbg_attach_w32eo_s(e->dbg));
       SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l2(e->dbg));
       SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l3(e->dbg));
       SG_CUDA((cudaError_t)sg::dbg_attach_psmooth_l4(e->dbg));
@@ -1037,7 +1048,7 @@ int stft_batch_impl(sg_engine* e, const void* pcm, int64_t n_clips, int64_t clip
 #ifdef SG_DEBUG
 // debug build only (not part of include/sgcore.h): mismatches per check site -- 0 exchange planes of the frame-pair
 // kernel, 1 its byte stage, 2 the state hand-off of the fused smoothing kernel (n_fft 2048), 3 the same of the part-warp
-// kernels (n_fft 1024 / 512 / 256) -- and, in the last entry, how many
+// kernels (n_fft 1024 / 512 / 256), 4 of the n_fft 4096 kernel -- and, in the last entry, how many
 // warp iterations ran with the checks armed
 extern "C" int sg_debug_counts(sg_engine* e, unsigned long long out[16]) {
   if (!e || !out) return fail(SG_ERR_INVALID_ARG, "null argument");

@@ -676,8 +676,8 @@ def test_fused_smoothing_kernel_on_frame_ranges_of_a_long_clip(engine):
     assert np.all(np.abs(two - got) <= 2e-5 * np.abs(got) + 1e-7 * got.max(axis=-1, keepdims=True))
 
 
-# ----------------------------------------------------------------------------- fused smoothing, n_fft 1024 / 512 / 256
-PS_KERNEL = {1024: "p16s", 512: "p8s", 256: "p4s"}
+# ----------------------------------------------------------------------------- fused smoothing, n_fft 4096 / 1024 / 512 / 256
+PS_KERNEL = {4096: "eo4096s", 1024: "p16s", 512: "p8s", 256: "p4s"}
 
 
 @pytest.mark.parametrize("n_fft,hop_div,n_clips,frames,extra,align", [
@@ -688,6 +688,10 @@ PS_KERNEL = {1024: "p16s", 512: "p8s", 256: "p4s"}
     (512, 8, 150, 90, 0, O.ALIGN_ANALYSER),
     (256, 4, 2, 2500, 3, O.ALIGN_VALID),         # eight pairs per warp, long chains
     (256, 8, 149, 61, 0, O.ALIGN_ANALYSER),      # clips shorter than one round of the CTA's warps
+    (4096, 4, 150, 40, 0, O.ALIGN_VALID),        # one frame per warp (even/odd kernel), several tasks per CTA
+    (4096, 4, 3, 200, 37, O.ALIGN_ANALYSER),     # zero history, chained segments of few clips
+    (4096, 8, 2, 150, 0, O.ALIGN_VALID),
+    (4096, 2, 149, 9, 4, O.ALIGN_VALID),         # clips shorter than one round of the CTA's warps
     (1024, 2, 4, 500, 9, O.ALIGN_ANALYSER),      # hop n_fft / 2
     (256, 2, 151, 77, 0, O.ALIGN_VALID),
     (512, 4, 3, 1, 0, O.ALIGN_VALID),            # a single frame per clip: one lone frame A, every other lane group idle
@@ -722,14 +726,14 @@ def test_fused_smoothing_part_warp_kernels_match_the_oracle(engine, n_fft, hop_d
             assert np.array_equal(got, O.colormap_lut()[got_u8])
 
 
-@pytest.mark.parametrize("n_fft", [1024, 512, 256])
+@pytest.mark.parametrize("n_fft", [4096, 1024, 512, 256])
 def test_fused_smoothing_part_warp_automatic_selection_and_paths_agree(engine, n_fft):
     """From ~2/3 of the SMs in clips the fused kernel is the automatic choice; the two-kernel path (forced by a
     device-resident batch below the threshold) agrees with it to rounding, and both with the oracle."""
     import torch
     rng = np.random.default_rng(n_fft)
     hop = n_fft // 4
-    clip_len = n_fft + 499 * hop
+    clip_len = n_fft + (499 if n_fft <= 1024 else 149) * hop
     x = torch.from_numpy((0.2 * rng.standard_normal((200, clip_len))).astype(np.float32)).cuda()
     opts = sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=0.75)
     frames = engine.num_frames(opts, clip_len)
@@ -749,7 +753,7 @@ def test_fused_smoothing_part_warp_automatic_selection_and_paths_agree(engine, n
     assert_mag_close(a[:2], ref)
 
 
-@pytest.mark.parametrize("n_fft", [1024, 256])
+@pytest.mark.parametrize("n_fft", [4096, 1024, 256])
 def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_fft):
     rng = np.random.default_rng(8)
     hop = n_fft // 4
