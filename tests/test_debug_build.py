@@ -29,7 +29,7 @@ def test_no_hand_off_reads_a_value_of_the_wrong_iteration():
     assert counts[15] > 1000, "the checks did not run"           # warp iterations with the tags armed
     assert counts[:15] == [0] * 15, f"tag mismatches per site: {counts[:15]}"
     assert "warp32x32x2p" in d["kernels"] and "warp32x32x2s" in d["kernels"]
-    assert {"p16s", "p8s", "p4s"} <= set(d["kernels"])
+    assert {"eo4096s", "p16s", "p8s", "p4s"} <= set(d["kernels"])
 
 
 def test_the_checker_sees_a_broken_turn_chain():
@@ -38,4 +38,5 @@ def test_the_checker_sees_a_broken_turn_chain():
     d = run_debug({"SG_DEBUG_BREAK_CHAIN": "1"})
     assert d["debug_counts"][2] > 0          # n_fft 2048 kernel
     assert d["debug_counts"][3] > 0          # part-warp kernels
+    assert d["debug_counts"][4] > 0          # n_fft 4096 kernel
     assert d["debug_counts"][0] == 0 and d["debug_counts"][1] == 0

@@ -54,8 +54,8 @@ eng.set_kernel_variant(7)
 for clips in (160, 3):
     eng.spectrogram(big[:clips], sg.Options(smoothingTimeConstant=0.8))
     seen.add(eng.last_kernel)
-# ... and the part-warp fused smoothing kernels (n_fft 1024 / 512 / 256): several steps per warp, chained segments
-for n_fft, clips in ((1024, 160), (512, 40), (256, 3)):
+# ... and the fused smoothing kernels of n_fft 4096 / 1024 / 512 / 256: several steps per warp, chained segments
+for n_fft, clips in ((4096, 160), (1024, 160), (512, 40), (256, 3)):
     eng.spectrogram(big[:clips], sg.Options(fftSize=n_fft, hop=n_fft // 4, smoothingTimeConstant=0.8))
     seen.add(eng.last_kernel)
 eng.set_kernel_variant(0)
