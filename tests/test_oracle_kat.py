@@ -124,6 +124,38 @@ def test_cross_check_torch_stft():
     assert np.allclose(got, ref, rtol=1e-9, atol=1e-12)
 
 
+def test_cross_check_torchaudio_spectrogram():
+    """torchaudio's Spectrogram transform with ITS OWN window function (Blackman, the AnalyserNode window): both the window
+    and the framed transform come from a third party here."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torch
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal(3 * 44100 // 10)
+    tr = torchaudio.transforms.Spectrogram(n_fft=2048, hop_length=512, power=1.0, center=False,
+                                           window_fn=lambda n: torch.blackman_window(n, periodic=True, dtype=torch.float64))
+    ref = tr(torch.from_numpy(x)).numpy().T[:, :1024] / 2048
+    got = O.spectrogram(x, O.Config(n_fft=2048, hop=512, output=O.OUT_F32_MAG))[0]
+    assert got.shape == ref.shape
+    assert np.allclose(got, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_cross_check_transformers_audio_utils():
+    """The numpy STFT behind the Hugging Face feature extractors (BASELINE config 4's shape: n_fft 400, hop 160, Hann),
+    amplitude and dB; its window function is its own as well."""
+    au = pytest.importorskip("transformers.audio_utils")
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(16000)
+    w = au.window_function(400, "hann", periodic=True)
+    ref = au.spectrogram(x, w, frame_length=400, hop_length=160, power=1.0, center=False, dtype=np.float64).T[:, :200] / 400
+    got = O.spectrogram(x, O.Config(n_fft=400, hop=160, window=O.WINDOW_HANN, output=O.OUT_F32_MAG))[0]
+    assert got.shape == ref.shape
+    # (that implementation keeps its frames in single precision whatever dtype it returns: agreement to float32 rounding)
+    assert np.allclose(got, ref, rtol=2e-6, atol=1e-8)
+    db = O.spectrogram(x, O.Config(n_fft=400, hop=160, window=O.WINDOW_HANN, output=O.OUT_F32_DB))[0]
+    near = ref >= ref.max(axis=-1, keepdims=True) * 1e-3
+    assert np.abs(db - 20 * np.log10(ref))[near].max() < 1e-4
+
+
 def test_parseval_rect_window():
     rng = np.random.default_rng(9)
     x = rng.standard_normal(2048)
