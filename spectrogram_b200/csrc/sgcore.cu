@@ -532,7 +532,8 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   if (even_odd) {
     if ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15)) return SG_OK;
   } else if ((pl.n_fft != sg::kW32N && !part_warp) ||
-             (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft)) {
+             (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft &&
+              !(cfg.hop == 160 && (pl.n_fft == 1024 || pl.n_fft == 512)))) {   // (hop 160: the 16 kHz speech front ends)
     return SG_OK;
   }
   const int bins = pl.n_fft / 2;

@@ -38,6 +38,11 @@ int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, con
       case 4: return launch_ps<OUT, 4>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 8
       case 8: return launch_ps<OUT, 8>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 4
       case 16: return launch_ps<OUT, 16>(g, x, p, ep, out, grid, device, st);   // hop = n_fft / 2
+#if SG_PAIR_LOG2L == 4
+      case 5: return launch_ps<OUT, 5>(g, x, p, ep, out, grid, device, st);     // n_fft 1024 at hop 160
+#elif SG_PAIR_LOG2L == 3
+      case 10: return launch_ps<OUT, 10>(g, x, p, ep, out, grid, device, st);   // n_fft 512 at hop 160
+#endif
       default: return -1;
     }
   });

@@ -753,6 +753,28 @@ def test_fused_smoothing_part_warp_automatic_selection_and_paths_agree(engine, n
     assert_mag_close(a[:2], ref)
 
 
+@pytest.mark.parametrize("n_fft,window", [(512, "hann"), (1024, "blackman")])
+def test_fused_smoothing_at_hop_160(engine, n_fft, window):
+    """The 16 kHz speech front-end hop (BASELINE config 2's shape) on the fused smoothing kernels."""
+    rng = np.random.default_rng(160 + n_fft)
+    n_clips, clip_len = 150, n_fft + 211 * 160 + 31
+    x = (0.1 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    w = {"hann": O.WINDOW_HANN, "blackman": O.WINDOW_BLACKMAN}[window]
+    sel = [0, 77, 149]
+    ref = O.spectrogram(x[sel], O.Config(n_fft=n_fft, hop=160, window=w, smoothing=0.6, output=O.OUT_F32_MAG))
+    for out in ("mag", "u8"):
+        engine.set_kernel_variant(7)
+        try:
+            got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=160, window=window, output=out, smoothingTimeConstant=0.6))
+        finally:
+            engine.set_kernel_variant(0)
+        assert engine.last_kernel == PS_KERNEL[n_fft]
+        if out == "mag":
+            assert_mag_close(got[sel], ref)
+        else:
+            assert_bytes_close(got[sel], O.finish(ref, O.Config(n_fft=n_fft, hop=160, window=w, smoothing=0.6)))
+
+
 @pytest.mark.parametrize("n_fft", [4096, 1024, 256])
 def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_fft):
     rng = np.random.default_rng(8)
