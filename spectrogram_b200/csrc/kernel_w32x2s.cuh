@@ -94,7 +94,11 @@ template <int OUT, int NW, int HOPJ, bool LATE, int K>
 __global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(XpShape<NW>::kMaxRegs)
 stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
-  constexpr int HOP = 64 * HOPJ, NLOAD = 32 + HOPJ;
+  // HOPJ > 0: hop = 64 HOPJ, frame B shares frame A's loads, the next pair is prefetched into registers.
+  // HOPJ == 0: any hop (441, 735 ... -- a display or feature cadence turned into a fixed hop): every pair loads its two
+  // frames directly at the top of its iteration (8-byte loads where the frame starts allow, else 4-byte), no prefetch.
+  constexpr int NLOAD = HOPJ ? 32 + HOPJ : 1;
+  const int HOP = HOPJ ? 64 * HOPJ : (int)g.hop;
   extern __shared__ float4 smem_raw[];
   float4* s_win4 = smem_raw;                                           // [16][32] (w2[l+32j], w2[l+32(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * 32);         // [5][32]  W_{32*2^u}^lane
@@ -138,7 +142,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
   auto pair_off = [&](const XsItem& c, int p) { return c.clip * g.clip_stride + g.start0 + (long long)(c.f0 + 2 * p) * HOP; };
   auto pair_fast = [&](const XsItem& c, int p, long long off) {
     const int t = c.f0 + 2 * p;
-    return c.valid && 2 * p + 1 < c.nfr && t >= t_lo && t <= t_hi && ((pcm_lo + ((unsigned)off << 2)) & 7u) == 0;
+    return HOPJ != 0 && c.valid && 2 * p + 1 < c.nfr && t >= t_lo && t <= t_hi && ((pcm_lo + ((unsigned)off << 2)) & 7u) == 0;
   };
   // the pair NW places further down this CTA's pair sequence.  Only (item index, pair index) is carried from one
   // iteration to the next; the item's fields are re-derived where they are needed (registers are what this kernel
@@ -168,7 +172,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
   {
     const XsItem c0 = xs_item(x, fpc, it);
     const float2* src = cur_fast ? reinterpret_cast<const float2*>(g.pcm + pair_off(c0, p)) + lane : idle_src;
-    static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
+    if constexpr (HOPJ != 0)
+      static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + 32 * m); });
   }
 
 #ifdef SG_DEBUG
@@ -181,15 +186,51 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     const bool has_b = 2 * p + 1 < cur.nfr;
     // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
     C2 a[32];
-    if (cur_fast) {
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
-        const float4 w = s_win4[j * 32 + lane];
-        window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
-                      make_float2(w.z, w.w));
-      });
+    bool loaded = false;
+    if constexpr (HOPJ != 0) {
+      if (cur_fast) {
+        static_for<0, 16>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);   // r1 == r0 + 1
+          const float4 w = s_win4[j * 32 + lane];
+          window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + (HOPJ ? HOPJ : 0)], s[j + 16 + (HOPJ ? HOPJ : 0)],
+                        make_float2(w.x, w.y), make_float2(w.z, w.w));
+        });
+        loaded = true;
+      }
     } else {
+      // any hop: both frames inside the clip -> unguarded loads, 8 bytes wide when both frame starts are 8-byte aligned
+      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
+      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
+      if (start_a >= 0 && start_b + kW32N <= g.clip_len) {
+        const float* __restrict__ fa_ = xa + start_a + 2 * lane;
+        const float* __restrict__ fb_ = xa + start_b + 2 * lane;
+        if (((reinterpret_cast<uintptr_t>(fa_) | reinterpret_cast<uintptr_t>(fb_)) & 7) == 0) {
+          const float2* __restrict__ pa = reinterpret_cast<const float2*>(fa_);
+          const float2* __restrict__ pb = reinterpret_cast<const float2*>(fb_);
+          static_for<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+            const float4 w = s_win4[j * 32 + lane];
+            window_stage1(a[r0], a[r1], __ldg(pa + 32 * j), __ldg(pa + 32 * (j + 16)), __ldg(pb + 32 * j), __ldg(pb + 32 * (j + 16)),
+                          make_float2(w.x, w.y), make_float2(w.z, w.w));
+          });
+        } else {
+          static_for<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+            const float4 w = s_win4[j * 32 + lane];
+            window_stage1(a[r0], a[r1], make_float2(__ldg(fa_ + 64 * j), __ldg(fa_ + 64 * j + 1)),
+                          make_float2(__ldg(fa_ + 64 * (j + 16)), __ldg(fa_ + 64 * (j + 16) + 1)),
+                          make_float2(__ldg(fb_ + 64 * j), __ldg(fb_ + 64 * j + 1)),
+                          make_float2(__ldg(fb_ + 64 * (j + 16)), __ldg(fb_ + 64 * (j + 16) + 1)), make_float2(w.x, w.y),
+                          make_float2(w.z, w.w));
+          });
+        }
+        loaded = true;
+      }
+    }
+    if (!loaded) {
       // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
       const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
       const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
@@ -284,7 +325,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
       // (1 - tau) |X| / N of both frames
       pk[i] = mul2(P2(sqrt_ftz(qk.v.x), sqrt_ftz(qk.v.y)), bc(x.mscale));
       pm[i] = mul2(P2(sqrt_ftz(qm.v.x), sqrt_ftz(qm.v.y)), bc(x.mscale));
-      if constexpr (!LATE) {
+      if constexpr (!LATE && HOPJ != 0) {
         static_for<(NLOAD * i) / 16, (NLOAD * (i + 1)) / 16>([&](auto mm) {
           constexpr int m = decltype(mm)::value;
           s[m] = ldg_nc_f2(nsrc + 32 * m);
@@ -415,7 +456,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
         });
       }
     }
-    if constexpr (LATE) {
+    if constexpr (LATE && HOPJ != 0) {
       static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + 32 * m); });
     }
 

@@ -531,7 +531,9 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   if (e->kernel_variant != 0 && e->kernel_variant != 7) return SG_OK;
   if (even_odd) {
     if ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15)) return SG_OK;
-  } else if ((pl.n_fft != sg::kW32N && !part_warp) ||
+  } else if (pl.n_fft == sg::kW32N) {
+    if (cfg.hop > 2048) return SG_OK;        // any hop up to n_fft (kernel_w32x2s.cuh: hop 1024 / 512 / 256 share loads)
+  } else if (!part_warp ||
              (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft &&
               !(cfg.hop == 160 && (pl.n_fft == 1024 || pl.n_fft == 512)))) {   // (hop 160: the 16 kHz speech front ends)
     return SG_OK;

@@ -30,7 +30,8 @@ int launch_w32x2s(int out_kind, const FrameGeom& g, const XsGeom& x, const W32Pl
     //  untangle 409 M; without waiting at all, wrong results, 518 M: the ordering itself costs 9 %)
     if (g.hop == 256) return launch_xs<OUT, 4, 8, true, 1>(g, x, p, ep, out, grid, device, st);
     if (g.hop == 1024) return launch_xs<OUT, 16, 8, true, 1>(g, x, p, ep, out, grid, device, st);
-    return launch_xs<OUT, 8, 8, true, 1>(g, x, p, ep, out, grid, device, st);
+    if (g.hop == 512) return launch_xs<OUT, 8, 8, true, 1>(g, x, p, ep, out, grid, device, st);
+    return launch_xs<OUT, 0, 8, true, 1>(g, x, p, ep, out, grid, device, st);       // any other hop: direct loads
   });
 }
 

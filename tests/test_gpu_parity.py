@@ -512,7 +512,7 @@ def test_random_shapes_agree_with_the_generic_kernel(engine, seed):
                 assert_bytes_close(got, ref_u8)
             else:
                 got_u8 = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, align=align, output="u8"))
-                assert np.array_equal(got, O.colormap_lut()[got_u8])
+                assert_rgba_is_lut_of(got, got_u8)
 
 @pytest.mark.parametrize("n_fft,hop", [(256, 64), (400, 160), (512, 160), (512, 128), (1024, 256), (1024, 128), (2048, 512),
                                        (4096, 1024), (600, 150)])
@@ -559,6 +559,18 @@ def test_time_parallel_scan_agrees_with_the_sequential_recurrence(engine):
             assert d.max() <= 1 and (d != 0).mean() < 1e-4
 
 
+def assert_rgba_is_lut_of(got_rgba, got_u8):
+    """RGBA output = the LUT of the byte output.  The two runs are cut into different chunks by the host pipeline (an RGBA
+    row is four times a byte row), so with tau > 0 they may take differently rounded smoothing paths (chained segments,
+    look-back, two-kernel): a byte on a rounding boundary may then differ by one level between them."""
+    lut = O.colormap_lut()
+    ok = (got_rgba == lut[got_u8]).all(-1)
+    if not ok.all():
+        up = (got_rgba == lut[np.clip(got_u8.astype(np.int32) + 1, 0, 255)]).all(-1)
+        dn = (got_rgba == lut[np.clip(got_u8.astype(np.int32) - 1, 0, 255)]).all(-1)
+        assert (ok | up | dn).all() and (~ok).mean() < 1e-4
+
+
 # ----------------------------------------------------------------------------- fused smoothing kernel (n_fft 2048, tau > 0)
 @pytest.mark.parametrize("n_clips,clip_len,hop,align", [
     (1, 2048 + 511 * 512, 512, O.ALIGN_VALID),        # few clips: aggregate pass + look-back + emit pass, even frames
@@ -568,6 +580,10 @@ def test_time_parallel_scan_agrees_with_the_sequential_recurrence(engine):
     (301, 2048 + 97 * 512, 512, O.ALIGN_ANALYSER),    # chained, odd frames per clip, several tasks per CTA
     (150, 2048 + 75 * 1024 + 5, 1024, O.ALIGN_ANALYSER),  # hop n/2 instantiation, chained
     (2, 2048 + 400 * 1024, 1024, O.ALIGN_VALID),      # hop n/2, look-back mode
+    (150, 2048 + 130 * 441 + 3, 441, O.ALIGN_ANALYSER),   # any-hop loader: odd hop (10 ms at 44.1 kHz), 4-byte loads
+    (3, 2048 + 600 * 735, 735, O.ALIGN_VALID),        # the reference's display cadence as a hop (1/60 s at 44.1 kHz), look-back
+    (151, 2048 + 90 * 160, 160, O.ALIGN_VALID),       # even hop, 8-byte loads
+    (149, 2048 * 40, 2048, O.ALIGN_VALID),            # frames that do not overlap
 ])
 def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, hop, align):
     rng = np.random.default_rng(n_clips)
@@ -592,7 +608,7 @@ def test_fused_smoothing_kernel_matches_the_oracle(engine, n_clips, clip_len, ho
             got_u8 = got
             assert_bytes_close(got[sel], O.finish(ref_mag, O.Config(n_fft=2048, hop=hop, smoothing=0.8, align=align)))
         else:
-            assert np.array_equal(got, O.colormap_lut()[got_u8])
+            assert_rgba_is_lut_of(got, got_u8)
 
 
 def test_fused_smoothing_chained_segments_are_the_sequential_arithmetic(engine):
@@ -723,7 +739,7 @@ def test_fused_smoothing_part_warp_kernels_match_the_oracle(engine, n_fft, hop_d
             got_u8 = got
             assert_bytes_close(got[sel], O.finish(ref_mag, O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, align=align)))
         else:
-            assert np.array_equal(got, O.colormap_lut()[got_u8])
+            assert_rgba_is_lut_of(got, got_u8)
 
 
 @pytest.mark.parametrize("n_fft", [4096, 1024, 512, 256])
