@@ -55,7 +55,11 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
   using T = typename OutElem<OUT>::type;
   using S = PairShape<LOG2L>;
   constexpr int L = S::L, N = S::N, M = S::M, NCOL = S::NCOL, NP = S::NP, PW = S::PW, NW = kPsWarps;
-  constexpr int HOP = 2 * L * HOPJ, NLOAD = 32 + HOPJ;
+  // HOPJ > 0: hop = 2 L HOPJ, frame B shares frame A's loads, the next step is prefetched into registers.
+  // HOPJ == 0: any hop -- every lane group loads its two frames directly at the top of the iteration (8-byte loads where
+  // the frame starts allow, else 4-byte), no prefetch.
+  constexpr int NLOAD = HOPJ ? 32 + HOPJ : 1;
+  const int HOP = HOPJ ? 2 * L * HOPJ : (int)g.hop;
   extern __shared__ float4 smem_raw[];
   float4* s_win4 = smem_raw;                                           // [16][L] (w2[t+Lj], w2[t+L(j+16)])
   float2* s_twb = reinterpret_cast<float2*>(s_win4 + 16 * L);          // [LOG2L][32]  W_{32*2^u}^col
@@ -97,7 +101,7 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
   auto pair_off = [&](const PsItem& c, int ta) { return c.clip * g.clip_stride + g.start0 + (long long)ta * HOP; };
   auto pair_fast = [&](const PsItem& c, int u, long long off) {
     const int p = u * PW + h, ta = c.f0 + 2 * p;
-    return c.valid && 2 * p + 1 < c.nfr && ta >= t_lo && ta <= t_hi && ((pcm_lo + ((unsigned)off << 2)) & 7u) == 0;
+    return HOPJ != 0 && c.valid && 2 * p + 1 < c.nfr && ta >= t_lo && ta <= t_hi && ((pcm_lo + ((unsigned)off << 2)) & 7u) == 0;
   };
   auto advance = [&](PsItem& c, int& u) {
     u += NW;
@@ -138,7 +142,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
   {
     const PsItem ci = ps_item(x, fpc, it);
     const float2* src = cur_fast ? reinterpret_cast<const float2*>(g.pcm + pair_off(ci, ci.f0 + 2 * (u * PW + h))) + t : idle_src;
-    static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + L * m); });
+    if constexpr (HOPJ != 0)
+      static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + L * m); });
   }
 
 #ifdef SG_DEBUG
@@ -152,15 +157,53 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     const int ta = cur.f0 + min(2 * p, cur.nfr - 1);          // idle lane groups recompute the segment's last frame
     // ---- steps 1-2 (+ FFT stage 1)
     C2 a[32];
-    if (cur_fast) {
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
-        const float4 w = s_win4[j * L + t];
-        window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
-                      make_float2(w.z, w.w));
-      });
+    bool loaded = false;
+    if constexpr (HOPJ != 0) {
+      if (cur_fast) {
+        static_for<0, 16>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+          const float4 w = s_win4[j * L + t];
+          window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
+                        make_float2(w.z, w.w));
+        });
+        loaded = true;
+      }
     } else {
+      // any hop: both frames inside the clip -> unguarded loads, 8 bytes wide when both frame starts are 8-byte aligned
+      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
+      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
+      if (start_a >= 0 && start_b + N <= g.clip_len) {
+        const float* __restrict__ fa_ = xa + start_a + 2 * t;
+        const float* __restrict__ fb_ = xa + start_b + 2 * t;
+        if (((reinterpret_cast<uintptr_t>(fa_) | reinterpret_cast<uintptr_t>(fb_)) & 7) == 0) {
+          const float2* __restrict__ pa = reinterpret_cast<const float2*>(fa_);
+          const float2* __restrict__ pb = reinterpret_cast<const float2*>(fb_);
+          static_for<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+            const float4 w = s_win4[j * L + t];
+            window_stage1(a[r0], a[r1], __ldg(pa + L * j), __ldg(pa + L * (j + 16)), __ldg(pb + L * j), __ldg(pb + L * (j + 16)),
+                          make_float2(w.x, w.y), make_float2(w.z, w.w));
+            if constexpr (j == 7) asm volatile("" ::: "memory");   // two batches of 32 loads: 64 at once do not fit the registers
+          });
+        } else {
+          static_for<0, 16>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+            const float4 w = s_win4[j * L + t];
+            window_stage1(a[r0], a[r1], make_float2(__ldg(fa_ + 2 * L * j), __ldg(fa_ + 2 * L * j + 1)),
+                          make_float2(__ldg(fa_ + 2 * L * (j + 16)), __ldg(fa_ + 2 * L * (j + 16) + 1)),
+                          make_float2(__ldg(fb_ + 2 * L * j), __ldg(fb_ + 2 * L * j + 1)),
+                          make_float2(__ldg(fb_ + 2 * L * (j + 16)), __ldg(fb_ + 2 * L * (j + 16) + 1)), make_float2(w.x, w.y),
+                          make_float2(w.z, w.w));
+            if constexpr (j == 7) asm volatile("" ::: "memory");
+          });
+        }
+        loaded = true;
+      }
+    }
+    if (!loaded) {
       // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
       const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
       const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
@@ -410,7 +453,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
       }
     }
     // the next step's loads, after the turn has been passed on
-    static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + L * m); });
+    if constexpr (HOPJ != 0)
+      static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(nsrc + L * m); });
 
     // ---- epilogue: X^ -> dB / byte / colour of both frames
     T* __restrict__ row_a = out + ((long long)cur.clip * x.out_clip_rows + ta) * (long long)M;

@@ -533,10 +533,8 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     if ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15)) return SG_OK;
   } else if (pl.n_fft == sg::kW32N) {
     if (cfg.hop > 2048) return SG_OK;        // any hop up to n_fft (kernel_w32x2s.cuh: hop 1024 / 512 / 256 share loads)
-  } else if (!part_warp ||
-             (cfg.hop * 2 != pl.n_fft && cfg.hop * 4 != pl.n_fft && cfg.hop * 8 != pl.n_fft &&
-              !(cfg.hop == 160 && (pl.n_fft == 1024 || pl.n_fft == 512)))) {   // (hop 160: the 16 kHz speech front ends)
-    return SG_OK;
+  } else if (!part_warp || cfg.hop > pl.n_fft) {
+    return SG_OK;        // (part-warp kernels: hop n/2, n/4, n/8 and 160 share loads, every other hop loads directly)
   }
   const int bins = pl.n_fft / 2;
   const int step_frames = part_warp ? 2 * (32 / (pl.n_fft / 64)) : even_odd ? 1 : 2;   // frames a warp takes at once

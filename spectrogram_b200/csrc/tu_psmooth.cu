@@ -26,12 +26,11 @@ static int launch_ps(const FrameGeom& g, const XsGeom& x, const PairPlan& p, con
 
 #define SG_CAT2(a, b) a##b
 #define SG_CAT(a, b) SG_CAT2(a, b)
-// hop = 2 * L * HOPJ samples; returns -1 when there is no instantiation for the hop
+// hop = 2 * L * HOPJ samples share the frames' loads; every other hop runs the direct-load instantiation (HOPJ = 0)
 int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, const XsGeom& x, const PairPlan& p,
                                           const Epilogue& ep, void* out, int grid, int device, cudaStream_t st) {
   constexpr int L = 1 << SG_PAIR_LOG2L;
-  if (g.hop % (2 * L)) return -1;
-  const int hopj = g.hop / (2 * L);
+  const int hopj = (g.hop % (2 * L)) ? 0 : g.hop / (2 * L);
   return dispatch_out(out_kind, [&](auto tag) {
     constexpr int OUT = decltype(tag)::value;
     switch (hopj) {
@@ -43,7 +42,7 @@ int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, con
 #elif SG_PAIR_LOG2L == 3
       case 10: return launch_ps<OUT, 10>(g, x, p, ep, out, grid, device, st);   // n_fft 512 at hop 160
 #endif
-      default: return -1;
+      default: return launch_ps<OUT, 0>(g, x, p, ep, out, grid, device, st);    // any other hop: direct loads
     }
   });
 }

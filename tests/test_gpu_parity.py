@@ -791,6 +791,31 @@ def test_fused_smoothing_at_hop_160(engine, n_fft, window):
             assert_bytes_close(got[sel], O.finish(ref, O.Config(n_fft=n_fft, hop=160, window=w, smoothing=0.6)))
 
 
+@pytest.mark.parametrize("n_fft,hop,n_clips,align", [
+    (1024, 441, 150, O.ALIGN_ANALYSER),     # odd hop: 4-byte loads, zero history
+    (512, 509, 3, O.ALIGN_VALID),           # hop just under the frame length (longer hops stay on the two-kernel path)
+    (256, 100, 152, O.ALIGN_VALID),         # even hop that is no multiple of the lane group's 8 samples: 8-byte loads
+    (1024, 200, 4, O.ALIGN_ANALYSER),
+])
+def test_fused_smoothing_part_warp_kernels_at_any_hop(engine, n_fft, hop, n_clips, align):
+    rng = np.random.default_rng(n_fft + hop)
+    clip_len = n_fft + 233 * hop + 5
+    x = (0.1 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    sel = np.unique(np.r_[0, n_clips // 2, n_clips - 1])
+    ref = O.spectrogram(x[sel], O.Config(n_fft=n_fft, hop=hop, smoothing=0.7, align=align, output=O.OUT_F32_MAG))
+    for out in ("mag", "u8"):
+        engine.set_kernel_variant(7)
+        try:
+            got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, output=out, smoothingTimeConstant=0.7, align=ALIGN[align]))
+        finally:
+            engine.set_kernel_variant(0)
+        assert engine.last_kernel == PS_KERNEL[n_fft]
+        if out == "mag":
+            assert_mag_close(got[sel], ref)
+        else:
+            assert_bytes_close(got[sel], O.finish(ref, O.Config(n_fft=n_fft, hop=hop, smoothing=0.7, align=align)))
+
+
 @pytest.mark.parametrize("n_fft", [4096, 1024, 256])
 def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_fft):
     rng = np.random.default_rng(8)
