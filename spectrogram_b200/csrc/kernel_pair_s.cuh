@@ -157,7 +157,23 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     const int ta = cur.f0 + min(2 * p, cur.nfr - 1);          // idle lane groups recompute the segment's last frame
     // ---- steps 1-2 (+ FFT stage 1)
     C2 a[32];
-    bool loaded = false;
+    auto load_guarded = [&] {
+      // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
+      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
+      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
+      auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xa + q) : 0.f; };
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+        const long long o0 = 2 * (t + L * j), o1 = 2 * (t + L * (j + 16));
+        const float4 w = s_win4[j * L + t];
+        window_stage1(a[r0], a[r1], make_float2(ld(start_a + o0), ld(start_a + o0 + 1)),
+                      make_float2(ld(start_a + o1), ld(start_a + o1 + 1)),
+                      make_float2(ld(start_b + o0), ld(start_b + o0 + 1)),
+                      make_float2(ld(start_b + o1), ld(start_b + o1 + 1)), make_float2(w.x, w.y),
+                      make_float2(w.z, w.w));
+      });
+    };
     if constexpr (HOPJ != 0) {
       if (cur_fast) {
         static_for<0, 16>([&](auto jj) {
@@ -167,7 +183,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
           window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + HOPJ], s[j + 16 + HOPJ], make_float2(w.x, w.y),
                         make_float2(w.z, w.w));
         });
-        loaded = true;
+      } else {
+        load_guarded();
       }
     } else {
       // any hop: both frames inside the clip -> unguarded loads, 8 bytes wide when both frame starts are 8-byte aligned
@@ -200,25 +217,9 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
             if constexpr (j == 7) asm volatile("" ::: "memory");
           });
         }
-        loaded = true;
+      } else {
+        load_guarded();
       }
-    }
-    if (!loaded) {
-      // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
-      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
-      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
-      auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xa + q) : 0.f; };
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
-        const long long o0 = 2 * (t + L * j), o1 = 2 * (t + L * (j + 16));
-        const float4 w = s_win4[j * L + t];
-        window_stage1(a[r0], a[r1], make_float2(ld(start_a + o0), ld(start_a + o0 + 1)),
-                      make_float2(ld(start_a + o1), ld(start_a + o1 + 1)),
-                      make_float2(ld(start_b + o0), ld(start_b + o0 + 1)),
-                      make_float2(ld(start_b + o1), ld(start_b + o1 + 1)), make_float2(w.x, w.y),
-                      make_float2(w.z, w.w));
-      });
     }
 
     // ---- pass 1, exchange, pass 2: kernel_pair.cuh

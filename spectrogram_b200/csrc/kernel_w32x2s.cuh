@@ -186,7 +186,23 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     const bool has_b = 2 * p + 1 < cur.nfr;
     // ---- steps 1-2 (+ FFT stage 1): window both frames, bit-reversed into registers
     C2 a[32];
-    bool loaded = false;
+    auto load_guarded = [&] {
+      // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
+      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
+      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
+      auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xa + q) : 0.f; };
+      static_for<0, 16>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
+        const long long o0 = 2 * (lane + 32 * j), o1 = 2 * (lane + 32 * (j + 16));
+        const float4 w = s_win4[j * 32 + lane];
+        window_stage1(a[r0], a[r1], make_float2(ld(start_a + o0), ld(start_a + o0 + 1)),
+                      make_float2(ld(start_a + o1), ld(start_a + o1 + 1)),
+                      make_float2(ld(start_b + o0), ld(start_b + o0 + 1)),
+                      make_float2(ld(start_b + o1), ld(start_b + o1 + 1)), make_float2(w.x, w.y),
+                      make_float2(w.z, w.w));
+      });
+    };
     if constexpr (HOPJ != 0) {
       if (cur_fast) {
         static_for<0, 16>([&](auto jj) {
@@ -196,7 +212,8 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
           window_stage1(a[r0], a[r1], s[j], s[j + 16], s[j + (HOPJ ? HOPJ : 0)], s[j + 16 + (HOPJ ? HOPJ : 0)],
                         make_float2(w.x, w.y), make_float2(w.z, w.w));
         });
-        loaded = true;
+      } else {
+        load_guarded();
       }
     } else {
       // any hop: both frames inside the clip -> unguarded loads, 8 bytes wide when both frame starts are 8-byte aligned
@@ -227,25 +244,9 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
                           make_float2(w.z, w.w));
           });
         }
-        loaded = true;
+      } else {
+        load_guarded();
       }
-    }
-    if (!loaded) {
-      // clip edges / zero history / a segment's odd last frame (frame B reads as frame A and is dropped)
-      const float* __restrict__ xa = g.pcm + cur.clip * g.clip_stride;
-      const long long start_a = g.start0 + (long long)ta * HOP, start_b = start_a + (has_b ? HOP : 0);
-      auto ld = [&](long long q) { return (q >= 0 && q < g.clip_len) ? __ldg(xa + q) : 0.f; };
-      static_for<0, 16>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr int r0 = bitrev(j, 5), r1 = bitrev(j + 16, 5);
-        const long long o0 = 2 * (lane + 32 * j), o1 = 2 * (lane + 32 * (j + 16));
-        const float4 w = s_win4[j * 32 + lane];
-        window_stage1(a[r0], a[r1], make_float2(ld(start_a + o0), ld(start_a + o0 + 1)),
-                      make_float2(ld(start_a + o1), ld(start_a + o1 + 1)),
-                      make_float2(ld(start_b + o0), ld(start_b + o0 + 1)),
-                      make_float2(ld(start_b + o1), ld(start_b + o1 + 1)), make_float2(w.x, w.y),
-                      make_float2(w.z, w.w));
-      });
     }
 
     // ---- pass 1, exchange, pass 2: kernel_w32x2p.cuh
