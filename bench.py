@@ -347,9 +347,9 @@ def measure_configs(torch, sg, eng, dev, stream, peak: float, quick: bool = Fals
     # the headline batch with smoothingTimeConstant 0.8 (AnalyserNode's default): the fused one-pass kernel
     out["config1_tau"] = entry(512, CLIP_LEN, sg.Options(fftSize=N_FFT, hop=HOP, output="u8", smoothingTimeConstant=0.8),
                                SR, 1, torch.uint8, False)
-    # the same batch shape at the other sizes (hop n/4): their fused one-pass kernels (kernel_pair_s.cuh, kernel_w32eo_s.cuh)
+    # the same batch shape at the other sizes (hop n/4): their fused one-pass kernels (kernel_pair_s.cuh, kernel_w32eo_s.cuh, kernel_wreg_s.cuh)
     out["config1_tau_sizes"] = {str(n): entry(512, CLIP_LEN, sg.Options(fftSize=n, hop=n // 4, output="u8", smoothingTimeConstant=0.8),
-                                              SR, 1, torch.uint8, False) for n in (256, 512, 1024, 4096)}
+                                              SR, 1, torch.uint8, False) for n in (256, 512, 1024, 4096, 8192)}
     # config 2: 1 h mono 16 kHz, n_fft 512, hop 160, float dB (Hann, as BASELINE.json names it)
     out["config2"] = entry(1, 16000 * (600 if quick else 3600), sg.Options(fftSize=512, hop=160, window="hann", output="db"),
                            16000, 4, torch.float32, False)

@@ -112,6 +112,9 @@ int launch_w32eo(int out_kind, int warps, const FrameGeom& g, const EoPlan& p, c
 // tau > 0 fused into the n_fft 4096 kernel (tu_w32eo_s.cu); XsGeom: kernel_w32x2s.cuh
 int launch_w32eo_s(int out_kind, const FrameGeom& g, const XsGeom& x, const EoPlan& p, const Epilogue& ep, void* out, int grid,
                    int device, cudaStream_t st);
+// tau > 0 fused into the register family (tu_regsmooth.cu): log2m 12 (n_fft 8192) or 11 (n_fft 4096)
+int launch_wreg_s(int out_kind, int log2m, const FrameGeom& g, const XsGeom& x, const WregPlan& p, const Epilogue& ep, void* out,
+                  int grid, int device, cudaStream_t st);
 
 // tu_pcm.cu: PCM ingestion (kernel_pcm.cuh)
 struct PcmGeom;

@@ -529,35 +529,42 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   const bool part_warp = pl.n_fft == 1024 || pl.n_fft == 512 || pl.n_fft == 256;
   const bool even_odd = pl.n_fft == sg::kEoN;      // kernel_w32eo_s.cuh: any hop that keeps frames 16-byte aligned
   if (e->kernel_variant != 0 && e->kernel_variant != 7) return SG_OK;
-  if (even_odd) {
-    if ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15)) return SG_OK;
+  // register family (kernel_wreg_s.cuh): n_fft 8192, and 4096 where the even/odd kernel's 16-byte loader cannot go
+  bool reg_family = pl.n_fft == 8192;
+  if (even_odd && ((cfg.hop & 3) || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(pcm_dev) & 15))) reg_family = true;
+  if (reg_family) {
+    if (cfg.hop > pl.n_fft || !pl.wreg_tw3) return SG_OK;
+  } else if (even_odd) {
   } else if (pl.n_fft == sg::kW32N) {
     if (cfg.hop > 2048) return SG_OK;        // any hop up to n_fft (kernel_w32x2s.cuh: hop 1024 / 512 / 256 share loads)
   } else if (!part_warp || cfg.hop > pl.n_fft) {
     return SG_OK;        // (part-warp kernels: hop n/2, n/4, n/8 and 160 share loads, every other hop loads directly)
   }
   const int bins = pl.n_fft / 2;
-  const int step_frames = part_warp ? 2 * (32 / (pl.n_fft / 64)) : even_odd ? 1 : 2;   // frames a warp takes at once
+  const int step_frames = reg_family ? 256 / (pl.n_fft / 64) : part_warp ? 2 * (32 / (pl.n_fft / 64)) : even_odd ? 1 : 2;   // frames taken at once
   // Every clip is one chain of segments, so the kernel keeps min(n_clips, SMs) CTAs busy.  Below ~2/3 of the SMs the
   // two-kernel path wins (64 x 60 s clips: 1.57 ms against 3.86 ms here, two clips 0.078 against 0.172 ms); variant 7
   // forces this kernel for any clip count (the tests use it to reach the look-back mode).
-  if (e->kernel_variant != 7 && 3 * n_clips < 2 * (long long)e->sm_count) return SG_OK;
+  if (e->kernel_variant != 7 && 3 * n_clips < 2 * (long long)e->sm_count * (reg_family ? 2 : 1)) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
-  const int grid_max = e->sm_count, nw = part_warp ? 8 * (step_frames / 2) : even_odd ? 4 : 12;   // pairs in one round of a CTA's warps
+  const int grid_max = (reg_family ? 2 : 1) * e->sm_count;                          // co-resident CTAs
+  const int nw = reg_family ? step_frames : part_warp ? 8 * (step_frames / 2) : even_odd ? 4 : 12;   // pairs in one round of a CTA
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
   auto even_up = [step_frames](long long v) { return (v + step_frames - 1) / step_frames * step_frames; };   // whole warp steps
   long long segs, seg_frames;
-  if (2 * n_clips <= grid_max && !part_warp && !even_odd) {
+  if (2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
     // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
     seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
     x.mode = 1;
   } else {
     // chained segments: pick the split that fills whole waves of CTAs best, segments of at least four rounds of pairs
+    // (fewer clips than co-resident CTAs: a clip's second segment would sit beside its first and only wait for it)
     long long best_s = 1;
     double best_eff = 0.0;
-    for (long long s_try = 1; s_try <= 64; ++s_try) {
+    const long long s_max = (n_clips < grid_max && e->kernel_variant != 7) ? 1 : 64;   // (variant 7: the tests want chains)
+    for (long long s_try = 1; s_try <= s_max; ++s_try) {
       const long long sf = even_up((nframes + s_try - 1) / s_try);
       if (s_try > 1 && sf < 8 * nw) break;
       const long long tasks = ((nframes + sf - 1) / sf) * n_clips, waves = (tasks + grid_max - 1) / grid_max;
@@ -595,7 +602,11 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
   const int grid = (int)std::min<long long>(tasks, grid_max);
-  if (even_odd) {
+  if (reg_family) {
+    const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
+    SG_CUDA((cudaError_t)sg::launch_wreg_s(cfg.output, pl.log2m, g, x, wp, ep, out, grid, e->device, st));
+    e->last_kernel = "wregs";
+  } else if (even_odd) {
     const sg::EoPlan eo{pl.win, pl.w32_tw2, pl.eo_tab};
     SG_CUDA((cudaError_t)sg::launch_w32eo_s(cfg.output, g, x, eo, ep, out, grid, e->device, st));
     e->last_kernel = "eo4096s";

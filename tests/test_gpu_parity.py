@@ -816,6 +816,62 @@ def test_fused_smoothing_part_warp_kernels_at_any_hop(engine, n_fft, hop, n_clip
             assert_bytes_close(got[sel], O.finish(ref, O.Config(n_fft=n_fft, hop=hop, smoothing=0.7, align=align)))
 
 
+@pytest.mark.parametrize("n_fft,hop,n_clips,frames,extra,align", [
+    (8192, 2048, 150, 21, 0, O.ALIGN_VALID),        # two frame slots per CTA, more tasks than CTAs
+    (8192, 2048, 3, 150, 77, O.ALIGN_ANALYSER),     # zero history, odd frame count, chained segments of few clips
+    (8192, 441, 2, 200, 0, O.ALIGN_VALID),          # odd hop: 4-byte loads
+    (8192, 4096, 301, 5, 3, O.ALIGN_VALID),         # clips of a few frames
+    (4096, 441, 150, 37, 0, O.ALIGN_ANALYSER),      # n_fft 4096 where the even/odd kernel cannot load: four slots per CTA
+    (4096, 735, 2, 301, 9, O.ALIGN_VALID),
+])
+def test_fused_smoothing_register_family_matches_the_oracle(engine, n_fft, hop, n_clips, frames, extra, align):
+    clip_len = n_fft + (frames - 1) * hop + extra
+    rng = np.random.default_rng(n_fft + n_clips + hop)
+    x = (0.05 * rng.standard_normal((n_clips, clip_len))).astype(np.float32)
+    x += O.chirp(clip_len, 48000.0, 100.0, 15000.0, 0.3)[None, :]
+    sel = np.unique(np.r_[0, min(1, n_clips - 1), n_clips // 2, n_clips - 1])
+    cfg = O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, align=align, output=O.OUT_F32_MAG)
+    ref_mag = O.spectrogram(x[sel], cfg)
+    for out in ("mag", "db", "u8", "rgba"):
+        opts = sg.Options(fftSize=n_fft, hop=hop, output=out, smoothingTimeConstant=0.8, align=ALIGN[align])
+        engine.set_kernel_variant(7)
+        try:
+            got = engine.spectrogram(x, opts)
+        finally:
+            engine.set_kernel_variant(0)
+        assert engine.last_kernel == "wregs"
+        if out == "mag":
+            assert_mag_close(got[sel], ref_mag)
+        elif out == "db":
+            assert_db_close(got[sel], ref_mag)
+        elif out == "u8":
+            got_u8 = got
+            assert_bytes_close(got[sel], O.finish(ref_mag, O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, align=align)))
+        else:
+            assert_rgba_is_lut_of(got, got_u8)
+
+
+def test_fused_smoothing_register_family_non_finite_frames_reset_the_state(engine):
+    rng = np.random.default_rng(81)
+    n_fft, hop = 8192, 2048
+    clip_len = n_fft + 40 * hop
+    x = (0.2 * rng.standard_normal((2, clip_len))).astype(np.float32)
+    x[0, n_fft + 10 * hop + 5] = np.nan        # four frames of clip 0 see the NaN
+    x[1, n_fft + 23 * hop + 9] = np.inf
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = O.spectrogram(x, O.Config(n_fft=n_fft, hop=hop, smoothing=0.8, output=O.OUT_F32_MAG))
+    engine.set_kernel_variant(7)
+    try:
+        got = engine.spectrogram(x, sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=0.8))
+    finally:
+        engine.set_kernel_variant(0)
+    assert engine.last_kernel == "wregs"
+    for c in (0, 1):
+        bad = np.all(ref[c] == 0, axis=1)
+        assert bad.sum() == 4 and np.all(got[c][bad] == 0)
+    assert_mag_close(got, ref)
+
+
 @pytest.mark.parametrize("n_fft", [4096, 1024, 256])
 def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_fft):
     rng = np.random.default_rng(8)
