@@ -140,8 +140,9 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
  * 2 = n_fft 2048 on the one-frame-per-warp kernel;  3 = n_fft 2048 on the register family (wreg);
  * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;
  * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM;
- * 7 = smoothingTimeConstant > 0 at n_fft 2048 / hop 512 or 256 on the fused one-pass kernel for ANY clip count
- *     (automatic selection takes it from ~2/3 of the SM count in clips, and the two-kernel path below that).
+ * 7 = smoothingTimeConstant > 0 on the fused one-pass kernel of the shape (n_fft 256 ... 8192, hop <= n_fft) for ANY
+ *     clip count (automatic selection takes it from ~2/3 of the co-resident CTA count in clips, and the two-kernel
+ *     path below that).
  * 3 also selects the register family for n_fft 256 / 512 / 1024 (which have dedicated kernels by default). */
 int sg_engine_set_kernel_variant(sg_engine* e, int variant);
 
