@@ -20,7 +20,7 @@ constexpr int kEsStateBytes = 16 * 32 * 16;
 constexpr int kEsSmemBytes = kEoTableBytes + kEsStateBytes + kEsWarps * 8 + kEsWarps * kXpPlaneBytes;
 
 struct EsItem {
-  int it, clip, seg, f0, nfr;
+  int it, clip, seg, f0, nfr, skip;   // skip: leading frames without output (XsGeom mode 2: warm-up of an independent segment)
   bool valid;
 };
 __device__ __forceinline__ EsItem es_item(const XsGeom& x, int fpc, int it) {
@@ -33,6 +33,12 @@ __device__ __forceinline__ EsItem es_item(const XsGeom& x, int fpc, int it) {
   c.clip = (int)(task - (unsigned)c.seg * n_clips);
   c.f0 = c.seg * x.seg_frames;
   c.nfr = min(x.seg_frames, fpc - c.f0);
+  c.skip = 0;
+  if (x.mode == 2) {
+    c.skip = min(c.f0, x.warm);
+    c.f0 -= c.skip;
+    c.nfr += c.skip;
+  }
   return c;
 }
 
@@ -224,7 +230,7 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
     const bool dirty = __any_sync(0xffffffffu, worst >= 0x7f800000u);
 
     // ---- the recurrence, in frame order
-    if (p == 0 && cur.seg > 0) {
+    if (p == 0 && cur.seg > 0 && x.mode != 2) {
       if (lane0)
         while (ld_acquire_u32(x.flags + (long long)(cur.seg - 1) * x.n_clips + cur.clip) != x.epoch) {}
       __syncwarp();
@@ -239,8 +245,9 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
 #endif
     if (p == 0) {
       // first frame of a work item: the state the segment starts from
-      if (cur.seg == 0) {
-        const float* __restrict__ si = x.state_in ? x.state_in + (long long)cur.clip * kEoBins : nullptr;
+      if (cur.seg == 0 || x.mode == 2) {
+        // (an independent segment starts from zero unless its warm-up reaches back to the clip's first frame)
+        const float* __restrict__ si = (x.state_in && cur.f0 == 0) ? x.state_in + (long long)cur.clip * kEoBins : nullptr;
         static_for<0, 16>([&](auto ii) {
           constexpr int i = decltype(ii)::value;
           int b[4];
@@ -283,6 +290,7 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
     if (p == cur.nfr - 1) {
       // last frame of a work item: hand the state to the next segment (or to the caller)
       if (cur.seg + 1 < x.segs) {
+        if (x.mode != 2) {
         const long long me = (long long)cur.seg * x.n_clips + cur.clip;
         float4* __restrict__ cv = reinterpret_cast<float4*>(x.carry) + me * 512 + lane;
         static_for<0, 16>([&](auto ii) {
@@ -292,6 +300,7 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
         __threadfence();
         __syncwarp();
         if (lane0) st_release_u32(x.flags + me, x.epoch);
+        }
       } else if (x.state_out != nullptr) {
         float* __restrict__ so = x.state_out + (long long)cur.clip * kEoBins;
         static_for<0, 16>([&](auto ii) {
@@ -306,6 +315,7 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
     // ---- epilogue: X^ -> dB / byte / colour; the next frame's loads ride in its 16 steps (two per step)
     T* __restrict__ row_lo = out + ((long long)cur.clip * x.out_clip_rows + tf) * (long long)kEoBins;
     T* __restrict__ row_hi = row_lo + 1024;
+    const bool emit = p >= cur.skip;              // warm-up frames of an independent segment leave no row
     if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {
       const P2 scale = bc(2.f * ep.byte_a);
       static_for<0, 16>([&](auto ii) {
@@ -320,7 +330,7 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
         if constexpr (OUT == kOutU8) {
           sb16[k] = (uint16_t)__byte_perm(k_lo, k_hi, 0x0040);
           sb16[mk] = (uint16_t)__byte_perm(m_lo, m_hi, 0x0040);
-        } else {
+        } else if (emit) {
           row_lo[k] = __ldg(ep.lut + k_lo); row_lo[mk] = __ldg(ep.lut + m_lo);
           row_hi[k] = __ldg(ep.lut + k_hi); row_hi[mk] = __ldg(ep.lut + m_hi);
         }
@@ -336,8 +346,10 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint4 w = s16[c * 32 + lane];
-          ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
-          rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+          if (emit) {
+            ra[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+            rb[c * 32 + lane] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+          }
         }
       }
     } else {
@@ -351,8 +363,10 @@ stft_w32eo_s_kernel(FrameGeom g, XsGeom x, EoPlan pl, Epilogue ep, typename OutE
           vk = mul2(P2(lg2_ftz(vk.v.x), lg2_ftz(vk.v.y)), bc(2.f * ep.db_scale));
           vm = mul2(P2(lg2_ftz(vm.v.x), lg2_ftz(vm.v.y)), bc(2.f * ep.db_scale));
         }
-        row_lo[k] = vk.v.x; row_hi[k] = vk.v.y;
-        row_hi[mk] = vm.v.x; row_lo[mk] = vm.v.y;
+        if (emit) {
+          row_lo[k] = vk.v.x; row_hi[k] = vk.v.y;
+          row_hi[mk] = vm.v.x; row_lo[mk] = vm.v.y;
+        }
         s[2 * i] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i));
         s[2 * i + 1] = ldg_nc_f4(nsrc + 32 * elem_of(2 * i + 1));
       });

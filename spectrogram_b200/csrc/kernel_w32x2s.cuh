@@ -40,7 +40,9 @@ struct XsGeom {
   float2* carry;           // [segs * n_clips][16][32]: state at the END of a segment (mode 1: its aggregate)
   unsigned* flags;         // [segs * n_clips]: == epoch once the carry is visible
   unsigned epoch;
-  int mode;
+  int mode;                // 0 chained segments, 1 aggregate pass + look-back + emit pass, 2 independent segments with warm-up
+  int warm;                // mode 2: frames (even, a multiple of the kernel's step) a segment runs ahead of its first output
+                           // row, from a zero state, so that nothing of what it missed survives in float32: tau^warm < 2^-149
 };
 
 constexpr int kXsStateBytes = 16 * 32 * 8;
@@ -53,21 +55,28 @@ struct XsShape {
 struct XsItem {
   int it;        // index in this CTA's item list
   int clip, seg;
-  int f0, nfr;   // first frame of the segment within the clip, frames in it
-  int kind;      // 0 chain, 1 aggregate pass (no output, zero state), 2 emit pass after look-back
+  int f0, nfr;   // first frame of the segment within the clip, frames in it (mode 2: including the warm-up frames)
+  int skip;      // leading frames that produce no output (mode 2 warm-up)
+  int kind;      // 0 chain, 1 aggregate pass (no output, zero state), 2 emit pass after look-back, 3 independent + warm-up
   bool valid;
 };
 __device__ __forceinline__ XsItem xs_item(const XsGeom& x, int fpc, int it) {
   XsItem c;
   c.it = it;
   const unsigned n_clips = (unsigned)x.n_clips, n_tasks = (unsigned)x.segs * n_clips;   // < 2^31 (host checks)
-  const unsigned task = x.mode == 0 ? blockIdx.x + (unsigned)it * gridDim.x : blockIdx.x;
-  c.valid = task < n_tasks && (x.mode == 0 || it < 2);
-  c.kind = x.mode == 0 ? 0 : 1 + it;
+  const unsigned task = x.mode != 1 ? blockIdx.x + (unsigned)it * gridDim.x : blockIdx.x;
+  c.valid = task < n_tasks && (x.mode != 1 || it < 2);
+  c.kind = x.mode == 0 ? 0 : x.mode == 1 ? 1 + it : 3;
   c.seg = (int)(task / n_clips);
   c.clip = (int)(task - (unsigned)c.seg * n_clips);
   c.f0 = c.seg * x.seg_frames;
   c.nfr = min(x.seg_frames, fpc - c.f0);
+  c.skip = 0;
+  if (x.mode == 2) {
+    c.skip = min(c.f0, x.warm);
+    c.f0 -= c.skip;
+    c.nfr += c.skip;
+  }
   return c;
 }
 
@@ -340,7 +349,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     //      kernel is pipelined K deep.  In the aggregate pass (kind 1) the sign bit of a state value records that a
     //      non-finite frame wiped that bin inside this segment (X^ itself is never negative): the look-back must
     //      then drop what came in from earlier segments.
-    if (p == 0 && cur.kind != 1 && cur.seg > 0) {
+    if (p == 0 && cur.kind != 1 && cur.kind != 3 && cur.seg > 0) {
       // the segments this one starts from must have been published (chain: the previous one; look-back: all of them)
       if (lane0) {
         for (int j = cur.kind == 0 ? cur.seg - 1 : 0; j < cur.seg; ++j)
@@ -361,8 +370,9 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
 #endif
       if (p == 0) {
         // first pair of a work item: the state the segment starts from
-        const float* __restrict__ si = (cur.kind != 1 && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
-        if (cur.kind == 1 || cur.seg == 0) {
+        // (an independent segment starts from zero unless its warm-up reaches back to the clip's first frame)
+        const float* __restrict__ si = (cur.kind != 1 && (cur.kind != 3 || cur.f0 == 0) && x.state_in) ? x.state_in + (long long)cur.clip * kW32M : nullptr;
+        if (cur.kind == 1 || cur.kind == 3 || cur.seg == 0) {
           static_for<i0, i1>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
             s_state[i * 32 + lane] =
@@ -436,7 +446,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     dbg_q += NW;
 #endif
     const bool last = p == (cur.nfr + 1) / 2 - 1;
-    if (last && !(cur.kind == 2 && cur.seg + 1 < x.segs)) {
+    if (last && !((cur.kind == 2 || cur.kind == 3) && cur.seg + 1 < x.segs)) {
       // last pair of a work item: hand the state to the next segment (or to the caller)
       if (cur.seg + 1 < x.segs) {
         const long long me = (long long)cur.seg * x.n_clips + cur.clip;
@@ -462,7 +472,7 @@ stft_w32x2s_kernel(FrameGeom g, XsGeom x, W32Plan pl, Epilogue ep, typename OutE
     }
 
     // ---- epilogue: X^ -> dB / byte / colour of both frames (nothing to write in the aggregate pass)
-    if (cur.kind != 1) {
+    if (cur.kind != 1 && 2 * p >= cur.skip) {
       T* __restrict__ row_a = out + ((long long)cur.clip * x.out_clip_rows + ta) * (long long)kW32M;
       T* __restrict__ row_b = row_a + kW32M;
       if constexpr (OUT == kOutU8 || OUT == kOutRgba8) {

@@ -23,7 +23,7 @@ struct WsShape {
 };
 
 struct WsItem {
-  int it, clip, seg, f0, nfr;
+  int it, clip, seg, f0, nfr, skip;   // skip: leading frames without output (XsGeom mode 2: warm-up of an independent segment)
   bool valid;
 };
 __device__ __forceinline__ WsItem ws_item(const XsGeom& x, int fpc, int it) {
@@ -36,6 +36,12 @@ __device__ __forceinline__ WsItem ws_item(const XsGeom& x, int fpc, int it) {
   c.clip = (int)(task - (unsigned)c.seg * n_clips);
   c.f0 = c.seg * x.seg_frames;
   c.nfr = min(x.seg_frames, fpc - c.f0);
+  c.skip = 0;
+  if (x.mode == 2) {
+    c.skip = min(c.f0, x.warm);
+    c.f0 -= c.skip;
+    c.nfr += c.skip;
+  }
   return c;
 }
 
@@ -84,7 +90,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
     const WsItem cur = ws_item(x, fpc, it);
     if (!cur.valid) break;
     const int ngroups = (cur.nfr + FPC - 1) / FPC;
-    if (cur.seg > 0) {
+    if (cur.seg > 0 && x.mode != 2) {
       // the segment this one starts from must have been published (every thread of slot 0 reads the carry below)
       if (tid == 0)
         while (ld_acquire_u32(x.flags + (long long)(cur.seg - 1) * x.n_clips + cur.clip) != x.epoch) {}
@@ -92,6 +98,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
     for (int gq = 0; gq < ngroups; ++gq) {
       const int p = gq * FPC + fs;
       const bool live = p < cur.nfr;
+      const bool store = live && p >= cur.skip;             // warm-up frames of an independent segment leave no row
       const int tf = cur.f0 + min(p, cur.nfr - 1);            // idle slots recompute the segment's last frame, store nothing
       const long long start = g.start0 + (long long)tf * g.hop;
       const float* __restrict__ xc = g.pcm + cur.clip * g.clip_stride;
@@ -230,8 +237,9 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
       first_turn = false;
       if (gq == 0 && fs == 0) {
         // first frame of a work item: the state the segment starts from
-        if (cur.seg == 0) {
-          const float* __restrict__ si = x.state_in ? x.state_in + (long long)cur.clip * M : nullptr;
+        if (cur.seg == 0 || x.mode == 2) {
+          // (an independent segment starts from zero unless its warm-up reaches back to the clip's first frame)
+          const float* __restrict__ si = (x.state_in && cur.f0 == 0) ? x.state_in + (long long)cur.clip * M : nullptr;
           static_for<0, 2 * NQ>([&](auto ee) {
             constexpr int e = decltype(ee)::value, xx = e / NQ, i = e % NQ;
             static_for<0, S3 / 2>([&](auto hh) {
@@ -264,6 +272,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
       if (live && p == cur.nfr - 1) {
         // last frame of a work item: hand the state to the next segment (or to the caller)
         if (cur.seg + 1 < x.segs) {
+          if (x.mode != 2) {
           const long long me = (long long)cur.seg * x.n_clips + cur.clip;
           float* __restrict__ cv = reinterpret_cast<float*>(x.carry) + me * M + t;
           static_for<0, 16>([&](auto uu) {
@@ -274,6 +283,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
           __threadfence();
           frame_sync();
           if (t == 0) st_release_u32(x.flags + me, x.epoch);
+          }
         } else if (x.state_out != nullptr) {
           float* __restrict__ so = x.state_out + (long long)cur.clip * M;
           static_for<0, 2 * NQ>([&](auto ee) {
@@ -302,7 +312,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
           if constexpr (OUT == kOutU8) {
             sb[k] = emit_smoothed<OUT>(mk_[u], ep);
             sb[mk] = emit_smoothed<OUT>(mm_[u], ep);
-          } else if (live) {
+          } else if (store) {
             row[k] = emit_smoothed<OUT>(mk_[u], ep);
             row[mk] = emit_smoothed<OUT>(mm_[u], ep);
           }
@@ -310,7 +320,7 @@ stft_wreg_s_kernel(FrameGeom g, XsGeom x, WregPlan pl, Epilogue ep, typename Out
       });
       frame_sync();
       if constexpr (OUT == kOutU8) {
-        if (live) {
+        if (store) {
           const uint4* s16 = reinterpret_cast<const uint4*>(sb);
           uint4* r16 = reinterpret_cast<uint4*>(row);
           r16[t] = s16[t];

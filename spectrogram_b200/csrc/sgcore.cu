@@ -545,16 +545,33 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   // Every clip is one chain of segments, so the kernel keeps min(n_clips, SMs) CTAs busy.  Below ~2/3 of the SMs the
   // two-kernel path wins (64 x 60 s clips: 1.57 ms against 3.86 ms here, two clips 0.078 against 0.172 ms); variant 7
   // forces this kernel for any clip count (the tests use it to reach the look-back mode).
-  if (e->kernel_variant != 7 && 3 * n_clips < 2 * (long long)e->sm_count * (reg_family ? 2 : 1)) return SG_OK;
   if ((bytes_out && cfg.min_db < -300.f) || nframes <= 0 || n_clips <= 0 || nframes > (1 << 28)) return SG_OK;
   const int grid_max = (reg_family ? 2 : 1) * e->sm_count;                          // co-resident CTAs
   const int nw = reg_family ? step_frames : part_warp ? 8 * (step_frames / 2) : even_odd ? 4 : 12;   // pairs in one round of a CTA
   sg::XsGeom x;
   x.n_clips = n_clips;
   x.out_clip_rows = out_clip_rows;
+  x.warm = 0;
   auto even_up = [step_frames](long long v) { return (v + step_frames - 1) / step_frames * step_frames; };   // whole warp steps
   long long segs, seg_frames;
-  if (2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
+  const bool few = 3 * n_clips < 2 * (long long)grid_max;
+  if (few && e->kernel_variant != 7) {
+    // Too few clips for one chain per CTA to fill the GPU.  Cut every clip into grid_max / n_clips INDEPENDENT segments:
+    // each starts `warm` frames early from a zero state and writes no rows until its own first frame.  What a segment
+    // misses of the true state has decayed by tau^warm < 2^-149 by then -- below the smallest float32 denormal, so the
+    // rows are those of the sequential recurrence (the same argument bounds the state a clip hands back).  The extra
+    // frames cost warm / seg_frames of the arithmetic; when that is more than the whole segment (long memories: tau close
+    // to 1; or very few frames per CTA) the two-kernel path is the better choice.
+    const double tau = (double)cfg.smoothing;
+    if (!(tau > 0.0 && tau < 1.0)) return SG_OK;
+    const long long warm = even_up((long long)std::ceil(103.3 / -std::log(tau)));
+    const long long per_clip = grid_max / n_clips;
+    if (per_clip < 2) return SG_OK;
+    seg_frames = even_up((nframes + per_clip - 1) / per_clip);
+    if (seg_frames < warm || seg_frames < 8 * nw || warm > (1 << 24)) return SG_OK;
+    x.mode = 2;
+    x.warm = (int)warm;
+  } else if (2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
     // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
     seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
     x.mode = 1;
@@ -585,7 +602,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   x.state_in = state;
   x.state_out = state;
   const size_t state_bytes = (size_t)n_clips * bins * sizeof(float);
-  if (x.mode == 1) {
+  if (x.mode != 0) {
     // the segments of a clip run concurrently and every one of them reads the clip's initial state: the final state
     // goes to a buffer of its own and is copied over afterwards
     SG_TRY(e->xs_state.reserve(state_bytes));
@@ -622,7 +639,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
     e->last_kernel = "warp32x32x2s";
   }
-  if (x.mode == 1) SG_CUDA(cudaMemcpyAsync(state, x.state_out, state_bytes, cudaMemcpyDeviceToDevice, st));
+  if (x.mode != 0) SG_CUDA(cudaMemcpyAsync(state, x.state_out, state_bytes, cudaMemcpyDeviceToDevice, st));
   e->launches++;
   *done = true;
   return SG_OK;

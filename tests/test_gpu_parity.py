@@ -893,3 +893,52 @@ def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_f
         bad = np.all(ref[c] == 0, axis=1)
         assert bad.sum() == 4 and np.all(got[c][bad] == 0)
     assert_mag_close(got, ref)
+
+
+# ----------------------------------------------------------------------------- few clips: independent segments with warm-up
+@pytest.mark.parametrize("n_fft,hop,n_clips,frames,tau,kernel", [
+    (2048, 512, 8, 4000, 0.6, "warp32x32x2s"),
+    (2048, 441, 5, 10000, 0.7, "warp32x32x2s"),      # odd hop
+    (1024, 256, 4, 6000, 0.5, "p16s"),
+    (256, 64, 2, 40000, 0.8, "p4s"),                 # two channels, the AnalyserNode default
+    (4096, 1024, 6, 4000, 0.5, "eo4096s"),
+    (8192, 2048, 10, 3000, 0.3, "wregs"),
+])
+def test_fused_smoothing_independent_segments_match_the_oracle(engine, n_fft, hop, n_clips, frames, tau, kernel):
+    """Fewer clips than CTAs: every clip is cut into segments that warm up from a zero state over enough frames for
+    tau^warm to vanish in float32 -- rows must be those of the sequential recurrence, also right behind a segment start."""
+    import torch
+    clip_len = n_fft + (frames - 1) * hop + 4        # (rows of whole 16-byte units: the n_fft 4096 kernel's loader wants them)
+    g = torch.Generator(device="cuda").manual_seed(n_fft + n_clips)
+    x = (torch.rand((n_clips, clip_len), device="cuda", generator=g) - 0.5).float() * 0.3
+    x[:, clip_len // 3: clip_len // 3 + 40 * hop] *= 30.0            # a loud burst: its tail must survive the segment borders
+    x[0, clip_len // 2: clip_len // 2 + (50 + n_fft // hop) * hop] = 0.0   # digital silence: rows decay geometrically (kept short
+                                                                            # enough to stay clear of float32 underflow)
+    opts = sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=tau)
+    assert engine.num_frames(opts, clip_len) == frames
+    out = torch.empty((n_clips, frames, n_fft // 2), dtype=torch.float32, device="cuda")
+    engine.spectrogram_device(x.data_ptr(), n_clips, clip_len, clip_len, opts, out.data_ptr())
+    engine.synchronize()
+    assert engine.last_kernel == kernel
+    sel = [0, n_clips - 1]
+    ref = O.spectrogram(x[sel].cpu().numpy(), O.Config(n_fft=n_fft, hop=hop, smoothing=tau, output=O.OUT_F32_MAG))
+    got = out[sel].cpu().numpy()
+    assert_mag_close(got, ref)
+    # the silent stretch: the recurrence decays geometrically and nothing but float32 rounding may separate the two
+    quiet = slice(clip_len // 2 // hop + n_fft // hop + 2, clip_len // 2 // hop + 45)
+    assert np.all(np.abs(got[0, quiet] - ref[0, quiet]) <= 2e-5 * ref[0, quiet] + 1e-30)
+    out8 = torch.empty((n_clips, frames, n_fft // 2), dtype=torch.uint8, device="cuda")
+    engine.spectrogram_device(x.data_ptr(), n_clips, clip_len, clip_len, sg.Options(fftSize=n_fft, hop=hop, output="u8", smoothingTimeConstant=tau),
+                              out8.data_ptr())
+    engine.synchronize()
+    assert_bytes_close(out8[sel].cpu().numpy(), O.finish(ref, O.Config(n_fft=n_fft, hop=hop, smoothing=tau)))
+
+
+def test_fused_smoothing_independent_segments_fall_back_for_long_memories(engine):
+    """tau close to 1: the warm-up would be longer than a segment, the two-kernel path stays."""
+    rng = np.random.default_rng(3)
+    x = (0.1 * rng.standard_normal((4, 2048 + 1999 * 512))).astype(np.float32)
+    got = engine.spectrogram(x, sg.Options(output="mag", smoothingTimeConstant=0.995))
+    assert engine.last_kernel != "warp32x32x2s"
+    ref = O.spectrogram(x[:1], O.Config(n_fft=2048, hop=512, smoothing=0.995, output=O.OUT_F32_MAG))
+    assert_mag_close(got[:1], ref)
