@@ -914,6 +914,7 @@ def test_fused_smoothing_independent_segments_match_the_oracle(engine, n_fft, ho
     x[:, clip_len // 3: clip_len // 3 + 40 * hop] *= 30.0            # a loud burst: its tail must survive the segment borders
     x[0, clip_len // 2: clip_len // 2 + (50 + n_fft // hop) * hop] = 0.0   # digital silence: rows decay geometrically (kept short
                                                                             # enough to stay clear of float32 underflow)
+    torch.cuda.synchronize()                     # torch filled x on its own stream; the engine runs on another
     opts = sg.Options(fftSize=n_fft, hop=hop, output="mag", smoothingTimeConstant=tau)
     assert engine.num_frames(opts, clip_len) == frames
     out = torch.empty((n_clips, frames, n_fft // 2), dtype=torch.float32, device="cuda")
