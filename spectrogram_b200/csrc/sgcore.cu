@@ -564,6 +564,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     // to 1; or very few frames per CTA) the two-kernel path is the better choice.
     const double tau = (double)cfg.smoothing;
     if (!(tau > 0.0 && tau < 1.0)) return SG_OK;
+    if (part_warp) return SG_OK;     // (the part-warp kernels have no such mode: kernel_pair_s.cuh says why)
     const long long warm = even_up((long long)std::ceil(103.3 / -std::log(tau)));
     const long long per_clip = grid_max / n_clips;
     if (per_clip < 2) return SG_OK;
@@ -619,6 +620,10 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   sg::FrameGeom g{pcm_dev, clip_len, clip_stride, nframes, n_clips * nframes, start0, cfg.n_fft, cfg.hop};
   const sg::Epilogue ep = make_epilogue(cfg, 2.0 * pl.n_fft, lut);
   const int grid = (int)std::min<long long>(tasks, grid_max);
+  static const bool trace = getenv("SG_TRACE_FUSED") != nullptr;
+  if (trace)
+    fprintf(stderr, "[sgcore] fused smoothing: n_fft %d hop %d clips %lld frames %lld mode %d segs %lld seg_frames %lld warm %d grid %d\n",
+            pl.n_fft, cfg.hop, n_clips, nframes, x.mode, segs, seg_frames, x.warm, grid);
   if (reg_family) {
     const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
     SG_CUDA((cudaError_t)sg::launch_wreg_s(cfg.output, pl.log2m, g, x, wp, ep, out, grid, e->device, st));
