@@ -322,6 +322,10 @@ def measure_configs(torch, sg, eng, dev, stream, peak: float, quick: bool = Fals
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def entry(n_clips, clip_len, opts, sr, elem_bytes, dtype, flush_l2, sigma=0.1):
+        # every entry starts from fresh device allocations: a tensor carved out of a block the caching allocator kept from
+        # an earlier, larger entry can land where the same call runs 1.7x slower (measured: 64 x 60 s clips at n_fft 2048,
+        # tau 0.8: 0.98 ms in fresh buffers, 1.7-1.8 ms in recycled ones; tools/bimodal_probe6.py)
+        torch.cuda.empty_cache()
         frames = eng.num_frames(opts, clip_len)
         bins = opts.fftSize // 2
         x = (torch.randn((n_clips, clip_len), device=dev, generator=gen) * sigma).float()
