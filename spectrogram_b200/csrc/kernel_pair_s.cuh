@@ -15,12 +15,6 @@
 // incoming state with one FMA, runs its two frames and -- last group only -- writes X^ back: 16 x (LDS.64, 6 FMA, STS.64),
 // as in the 2048 kernel.  The scan rounds differently from the frame-by-frame recurrence (a few ulp; the tolerance of
 // tests/_tol.py, like the two-kernel path's chunk sums).
-// Chained segments only.  The independent-segment mode of the other fused kernels (XsGeom mode 2, warm-up from a zero
-// state) was built here too and taken out again: as a run-time switch its three extra integer operations per item and two
-// extra store predicates cost the chained kernel 9 % (785 vs 860 M frames/s at n_fft 1024 -- at 254 registers the loop state
-// is rematerialised from the item every iteration), and as a template parameter the warm-up instantiation ran its turn ring
-// at half speed (404 M where 690 M were expected; 35 % of the samples in the try_wait spin, `no_instruction` 2.3 per issue).
-// Few clips at these sizes stay on the two-kernel path.
 // [SPEC] "non-finite X^ -> 0" is applied per frame: if any power of the step is Inf/NaN (one vote per step) the groups
 // take their turn one after the other through the shared state with the per-value rule.
 #pragma once
@@ -39,9 +33,16 @@ struct PsShape {
 };
 
 struct PsItem {
-  int it, clip, seg, f0, nfr;
+  int it, clip, seg, f0, nfr, skip;   // skip: leading frames without output (XsGeom mode 2: warm-up of an independent segment)
   bool valid;
 };
+// WARM instantiations serve XsGeom mode 2 (independent segments with a warm-up from a zero state, kernel_w32x2s.cuh).  They
+// are separate instantiations because the chained kernel cannot afford the mode as a run-time switch -- three more integer
+// operations per item and two more store predicates cost it 9 % (785 vs 860 M frames/s at n_fft 1024: at 254 registers the
+// loop state is rematerialised from the item every iteration) -- and they keep their `x.mode == 2` tests as run-time tests:
+// the same code with those tests folded at compile time ran its turn ring at half speed (404 vs 697 M frames/s; 35 % of the
+// samples in the try_wait spin, `no_instruction` 2.3 per issue), for a reason the profile shows but does not explain.
+template <bool WARM>
 __device__ __forceinline__ PsItem ps_item(const XsGeom& x, int fpc, int it) {
   PsItem c;
   c.it = it;
@@ -52,10 +53,16 @@ __device__ __forceinline__ PsItem ps_item(const XsGeom& x, int fpc, int it) {
   c.clip = (int)(task - (unsigned)c.seg * n_clips);
   c.f0 = c.seg * x.seg_frames;
   c.nfr = min(x.seg_frames, fpc - c.f0);
+  c.skip = 0;
+  if (WARM && x.mode == 2) {
+    c.skip = min(c.f0, x.warm);
+    c.f0 -= c.skip;
+    c.nfr += c.skip;
+  }
   return c;
 }
 
-template <int OUT, int LOG2L, int HOPJ>
+template <int OUT, int LOG2L, int HOPJ, bool WARM = false>
 __global__ void __launch_bounds__(kPsWarps * 32, 1)
 stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename OutElem<OUT>::type* __restrict__ out) {
   using T = typename OutElem<OUT>::type;
@@ -113,14 +120,14 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     u += NW;
     while (c.valid && u >= steps_of(c)) {
       u -= steps_of(c);
-      c = ps_item(x, fpc, c.it + 1);
+      c = ps_item<WARM>(x, fpc, c.it + 1);
     }
   };
 
   int it, u = warp - NW;
   bool cur_fast;
   {
-    PsItem c0 = ps_item(x, fpc, 0);
+    PsItem c0 = ps_item<WARM>(x, fpc, 0);
     advance(c0, u);
     if (!c0.valid) return;
     it = c0.it;
@@ -146,7 +153,7 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
   float2 s[NLOAD];
   const float2* idle_src = reinterpret_cast<const float2*>(pl.win) + t;   // readable past the window (build_plan)
   {
-    const PsItem ci = ps_item(x, fpc, it);
+    const PsItem ci = ps_item<WARM>(x, fpc, it);
     const float2* src = cur_fast ? reinterpret_cast<const float2*>(g.pcm + pair_off(ci, ci.f0 + 2 * (u * PW + h))) + t : idle_src;
     if constexpr (HOPJ != 0)
       static_for<0, NLOAD>([&](auto mm) { constexpr int m = decltype(mm)::value; s[m] = ldg_nc_f2(src + L * m); });
@@ -157,9 +164,10 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
   unsigned* dbg_tags = dbg_cta_tags();          // one tag per state slot (i, t): the step that wrote it, plus one
 #endif
   while (true) {
-    const PsItem cur = ps_item(x, fpc, it);
+    const PsItem cur = ps_item<WARM>(x, fpc, it);
     const int p = u * PW + h;
     const bool active = 2 * p < cur.nfr, has_b = 2 * p + 1 < cur.nfr;
+    const bool store_a = active && (!WARM || 2 * p >= cur.skip), store_b = has_b && (!WARM || 2 * p >= cur.skip);   // (skip is even)
     const int ta = cur.f0 + min(2 * p, cur.nfr - 1);          // idle lane groups recompute the segment's last frame
     // ---- steps 1-2 (+ FFT stage 1)
     C2 a[32];
@@ -365,7 +373,7 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     }
 
     // ---- the recurrence, in step order
-    if (u == 0 && cur.seg > 0) {
+    if (u == 0 && cur.seg > 0 && !(WARM && x.mode == 2)) {
       // the segment this one starts from must have been published
       if (lane == 0)
         while (ld_acquire_u32(x.flags + (long long)(cur.seg - 1) * x.n_clips + cur.clip) != x.epoch) {}
@@ -383,8 +391,9 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     if (u == 0) {
       // first step of a work item: the state the segment starts from
       if (h == 0) {
-        if (cur.seg == 0) {
-          const float* __restrict__ si = x.state_in ? x.state_in + (long long)cur.clip * M : nullptr;
+        if (cur.seg == 0 || (WARM && x.mode == 2)) {
+          // (an independent segment starts from zero unless its warm-up reaches back to the clip's first frame)
+          const float* __restrict__ si = (x.state_in && cur.f0 == 0) ? x.state_in + (long long)cur.clip * M : nullptr;
           static_for<0, 16>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
             int k, mk;
@@ -442,12 +451,14 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
     if (u == steps_of(cur) - 1 && h == PW - 1) {
       // last step of a work item: hand the state to the next segment (or to the caller)
       if (cur.seg + 1 < x.segs) {
+        if (!(WARM && x.mode == 2)) {
         const long long me = (long long)cur.seg * x.n_clips + cur.clip;
         float2* __restrict__ cv = x.carry + me * (16 * L) + t;
         static_for<0, 16>([&](auto ii) { constexpr int i = decltype(ii)::value; cv[i * L] = fin[i]; });
         __threadfence();
         __syncwarp((0xffffffffu >> (32 - L)) << (L * (PW - 1)));
         if (t == 0) st_release_u32(x.flags + me, x.epoch);
+        }
       } else if (x.state_out != nullptr) {
         float* __restrict__ so = x.state_out + (long long)cur.clip * M;
         static_for<0, 16>([&](auto ii) {
@@ -479,9 +490,9 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
         if constexpr (OUT == kOutU8) {
           sb16[k] = (uint16_t)__byte_perm(kA, kB, 0x0040);
           sb16[mk] = (uint16_t)__byte_perm(mA, mB, 0x0040);
-        } else if (active) {
+        } else if (store_a) {
           row_a[k] = __ldg(ep.lut + kA); row_a[mk] = __ldg(ep.lut + mA);
-          if (has_b) { row_b[k] = __ldg(ep.lut + kB); row_b[mk] = __ldg(ep.lut + mB); }
+          if (store_b) { row_b[k] = __ldg(ep.lut + kB); row_b[mk] = __ldg(ep.lut + mB); }
         }
       });
       if constexpr (OUT == kOutU8) {
@@ -492,8 +503,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint4 w = s16[c * L + t];
-          if (active) ra[c * L + t] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
-          if (has_b) rb[c * L + t] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+          if (store_a) ra[c * L + t] = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+          if (store_b) rb[c * L + t] = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
         }
       }
     } else {
@@ -518,8 +529,8 @@ stft_pair_s_kernel(FrameGeom g, XsGeom x, PairPlan pl, Epilogue ep, typename Out
       uint4* rb = reinterpret_cast<uint4*>(row_b);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {          // M / 4 = 8 L 16-byte words per row
-        if (active) ra[c * L + t] = s4[c * L + t];
-        if (has_b) rb[c * L + t] = s4[M / 4 + c * L + t];
+        if (store_a) ra[c * L + t] = s4[c * L + t];
+        if (store_b) rb[c * L + t] = s4[M / 4 + c * L + t];
       }
     }
     __syncwarp();

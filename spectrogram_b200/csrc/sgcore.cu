@@ -564,7 +564,7 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     // to 1; or very few frames per CTA) the two-kernel path is the better choice.
     const double tau = (double)cfg.smoothing;
     if (!(tau > 0.0 && tau < 1.0)) return SG_OK;
-    if (part_warp) return SG_OK;     // (the part-warp kernels have no such mode: kernel_pair_s.cuh says why)
+    if (part_warp && cfg.hop * 4 != pl.n_fft) return SG_OK;     // (the part-warp kernels instantiate this mode for hop n/4 only)
     const long long warm = even_up((long long)std::ceil(103.3 / -std::log(tau)));
     const long long per_clip = grid_max / n_clips;
     if (per_clip < 2) return SG_OK;

@@ -8,19 +8,19 @@
 
 namespace sg {
 
-template <int OUT, int HOPJ>
+template <int OUT, int HOPJ, bool WARM = false>
 static int launch_ps(const FrameGeom& g, const XsGeom& x, const PairPlan& p, const Epilogue& ep, void* out, int grid,
                      int device, cudaStream_t st) {
   constexpr int LOG2L = SG_PAIR_LOG2L;
   using T = typename OutElem<OUT>::type;
   constexpr int smem = PsShape<LOG2L>::kSmemBytes;
-  const cudaError_t rc = ensure_dynamic_smem<stft_pair_s_kernel<OUT, LOG2L, HOPJ>>(smem, device);
+  const cudaError_t rc = ensure_dynamic_smem<stft_pair_s_kernel<OUT, LOG2L, HOPJ, WARM>>(smem, device);
   if (rc != cudaSuccess) return (int)rc;
   // CTAs wait for one another (a segment's first step for its predecessor's carry): a cooperative launch guarantees
   // that the whole grid (<= one CTA per SM) is resident at the same time, or fails instead of hanging
   T* out_t = (T*)out;
   void* args[] = {(void*)&g, (void*)&x, (void*)&p, (void*)&ep, (void*)&out_t};
-  return (int)cudaLaunchCooperativeKernel((const void*)stft_pair_s_kernel<OUT, LOG2L, HOPJ>, dim3(grid), dim3(kPsWarps * 32),
+  return (int)cudaLaunchCooperativeKernel((const void*)stft_pair_s_kernel<OUT, LOG2L, HOPJ, WARM>, dim3(grid), dim3(kPsWarps * 32),
                                           args, smem, st);
 }
 
@@ -33,6 +33,10 @@ int SG_CAT(launch_pair_s_l, SG_PAIR_LOG2L)(int out_kind, const FrameGeom& g, con
   const int hopj = (g.hop % (2 * L)) ? 0 : g.hop / (2 * L);
   return dispatch_out(out_kind, [&](auto tag) {
     constexpr int OUT = decltype(tag)::value;
+    if (x.mode == 2) {      // independent segments with a warm-up: instantiated for hop = n_fft / 4 only
+      if (hopj != 8) return -1;
+      return launch_ps<OUT, 8, true>(g, x, p, ep, out, grid, device, st);
+    }
     switch (hopj) {
       case 4: return launch_ps<OUT, 4>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 8
       case 8: return launch_ps<OUT, 8>(g, x, p, ep, out, grid, device, st);     // hop = n_fft / 4

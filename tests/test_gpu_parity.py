@@ -899,6 +899,8 @@ def test_fused_smoothing_part_warp_non_finite_frames_reset_the_state(engine, n_f
 @pytest.mark.parametrize("n_fft,hop,n_clips,frames,tau,kernel", [
     (2048, 512, 8, 4000, 0.6, "warp32x32x2s"),
     (2048, 441, 5, 10000, 0.7, "warp32x32x2s"),      # odd hop
+    (1024, 256, 4, 6000, 0.5, "p16s"),
+    (256, 64, 2, 40000, 0.8, "p4s"),                 # two channels, the AnalyserNode default
     (4096, 1024, 6, 4000, 0.5, "eo4096s"),
     (8192, 2048, 10, 3000, 0.3, "wregs"),
 ])
