@@ -141,8 +141,9 @@ int sg_stft_batch_device(sg_engine* e, const float* pcm_dev, int64_t n_clips, in
  * 4 = n_fft 2048 on the TMA-staged frame-pair kernel;
  * 6 = the register-pipelined frame-pair kernel with 8 instead of 12 warps per SM;
  * 7 = smoothingTimeConstant > 0 on the fused one-pass kernel of the shape (n_fft 256 ... 8192, hop <= n_fft) for ANY
- *     clip count (automatic selection takes it from ~2/3 of the co-resident CTA count in clips, and the two-kernel
- *     path below that).
+ *     clip count, with chained segments (automatic selection runs one chain per clip from ~45 % of the co-resident CTA
+ *     count in clips, independent segments with a warm-up below that when a segment is at least as long as its warm-up,
+ *     and the two-kernel path otherwise).
  * 3 also selects the register family for n_fft 256 / 512 / 1024 (which have dedicated kernels by default). */
 int sg_engine_set_kernel_variant(sg_engine* e, int variant);
 

@@ -555,25 +555,32 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   auto even_up = [step_frames](long long v) { return (v + step_frames - 1) / step_frames * step_frames; };   // whole warp steps
   long long segs, seg_frames;
   const bool few = 3 * n_clips < 2 * (long long)grid_max;
+  bool warm_up = false;
   if (few && e->kernel_variant != 7) {
     // Too few clips for one chain per CTA to fill the GPU.  Cut every clip into grid_max / n_clips INDEPENDENT segments:
     // each starts `warm` frames early from a zero state and writes no rows until its own first frame.  What a segment
     // misses of the true state has decayed by tau^warm < 2^-149 by then -- below the smallest float32 denormal, so the
     // rows are those of the sequential recurrence (the same argument bounds the state a clip hands back).  The extra
     // frames cost warm / seg_frames of the arithmetic; when that is more than the whole segment (long memories: tau close
-    // to 1; or very few frames per CTA) the two-kernel path is the better choice.
+    // to 1; or very few frames per CTA) it is not worth it.
     const double tau = (double)cfg.smoothing;
-    if (!(tau > 0.0 && tau < 1.0)) return SG_OK;
-    if (part_warp && cfg.hop * 4 != pl.n_fft) return SG_OK;     // (the part-warp kernels instantiate this mode for hop n/4 only)
-    const long long warm = even_up((long long)std::ceil(103.3 / -std::log(tau)));
     const long long per_clip = grid_max / n_clips;
-    if (per_clip < 2) return SG_OK;
-    seg_frames = even_up((nframes + per_clip - 1) / per_clip);
-    if (seg_frames < warm || seg_frames < 8 * nw || warm > (1 << 24)) return SG_OK;
-    x.mode = 2;
-    x.warm = (int)warm;
-  } else if (2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
-    // few clips: every segment gets a CTA of its own (aggregate pass, look-back, emit pass)
+    if (tau > 0.0 && tau < 1.0 && per_clip >= 2 && !(part_warp && cfg.hop * 4 != pl.n_fft)) {   // (part-warp kernels: hop n/4 only)
+      const long long warm = even_up((long long)std::ceil(103.3 / -std::log(tau)));
+      seg_frames = even_up((nframes + per_clip - 1) / per_clip);
+      if (seg_frames >= warm && seg_frames >= 8 * nw && warm <= (1 << 24)) {
+        warm_up = true;
+        x.mode = 2;
+        x.warm = (int)warm;
+      }
+    }
+    // otherwise: one chain per clip on n_clips CTAs still beats the two-kernel path from ~45 % of the CTAs up (the
+    // two-kernel path runs at ~0.4 of the fused kernels' rate); below that, the two-kernel path
+    if (!warm_up && 20 * n_clips < 9 * (long long)grid_max) return SG_OK;
+  }
+  if (warm_up) {
+  } else if (e->kernel_variant == 7 && 2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
+    // (tests only: it loses to every alternative) every segment gets a CTA of its own: aggregate pass, look-back, emit pass
     seg_frames = std::max<long long>(2 * nw, even_up((nframes + grid_max / n_clips - 1) / (grid_max / n_clips)));
     x.mode = 1;
   } else {
