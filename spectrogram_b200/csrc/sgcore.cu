@@ -576,7 +576,10 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
     }
     // otherwise: one chain per clip on n_clips CTAs still beats the two-kernel path from ~45 % of the CTAs up (the
     // two-kernel path runs at ~0.4 of the fused kernels' rate); below that, the two-kernel path
-    if (!warm_up && 20 * n_clips < 9 * (long long)grid_max) return SG_OK;
+    // (break-even against each family's two-kernel rate: 0.40 of the fused rate at n_fft 2048 and 4096, 0.48 for the
+    //  part-warp kernels, 0.65 for the register family)
+    const long long min_chain = reg_family ? (2 * (long long)grid_max + 2) / 3 : part_warp ? grid_max / 2 : (9 * (long long)grid_max + 19) / 20;
+    if (!warm_up && n_clips < min_chain) return SG_OK;
   }
   if (warm_up) {
   } else if (e->kernel_variant == 7 && 2 * n_clips <= grid_max && pl.n_fft == sg::kW32N) {
