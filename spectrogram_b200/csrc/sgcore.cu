@@ -634,26 +634,35 @@ int launch_fused_smoothing(sg_engine* e, const Plan& pl, const sg_stft_config& c
   if (trace)
     fprintf(stderr, "[sgcore] fused smoothing: n_fft %d hop %d clips %lld frames %lld mode %d segs %lld seg_frames %lld warm %d grid %d\n",
             pl.n_fft, cfg.hop, n_clips, nframes, x.mode, segs, seg_frames, x.warm, grid);
+  int rc;
+  const char* name;
   if (reg_family) {
     const sg::WregPlan wp{pl.win, pl.w32_tw2, pl.wreg_tw3, pl.ut};
-    SG_CUDA((cudaError_t)sg::launch_wreg_s(cfg.output, pl.log2m, g, x, wp, ep, out, grid, e->device, st));
-    e->last_kernel = "wregs";
+    rc = sg::launch_wreg_s(cfg.output, pl.log2m, g, x, wp, ep, out, grid, e->device, st);
+    name = "wregs";
   } else if (even_odd) {
     const sg::EoPlan eo{pl.win, pl.w32_tw2, pl.eo_tab};
-    SG_CUDA((cudaError_t)sg::launch_w32eo_s(cfg.output, g, x, eo, ep, out, grid, e->device, st));
-    e->last_kernel = "eo4096s";
+    rc = sg::launch_w32eo_s(cfg.output, g, x, eo, ep, out, grid, e->device, st);
+    name = "eo4096s";
   } else if (part_warp) {
     const sg::PairPlan pp{pl.win, pl.pair_twb, pl.ut};
-    const int rc = pl.n_fft == 1024 ? sg::launch_pair_s_l4(cfg.output, g, x, pp, ep, out, grid, e->device, st)
-                   : pl.n_fft == 512 ? sg::launch_pair_s_l3(cfg.output, g, x, pp, ep, out, grid, e->device, st)
-                                     : sg::launch_pair_s_l2(cfg.output, g, x, pp, ep, out, grid, e->device, st);
-    SG_CUDA((cudaError_t)rc);
-    e->last_kernel = pl.n_fft == 1024 ? "p16s" : pl.n_fft == 512 ? "p8s" : "p4s";
+    rc = pl.n_fft == 1024 ? sg::launch_pair_s_l4(cfg.output, g, x, pp, ep, out, grid, e->device, st)
+         : pl.n_fft == 512 ? sg::launch_pair_s_l3(cfg.output, g, x, pp, ep, out, grid, e->device, st)
+                           : sg::launch_pair_s_l2(cfg.output, g, x, pp, ep, out, grid, e->device, st);
+    name = pl.n_fft == 1024 ? "p16s" : pl.n_fft == 512 ? "p8s" : "p4s";
   } else {
     const sg::W32Plan wp{pl.win, pl.w32_tw2, pl.w32_ut};
-    SG_CUDA((cudaError_t)sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st));
-    e->last_kernel = "warp32x32x2s";
+    rc = sg::launch_w32x2s(cfg.output, g, x, wp, ep, out, grid, e->device, st);
+    name = "warp32x32x2s";
   }
+  if (rc == (int)cudaErrorCooperativeLaunchTooLarge || rc == (int)cudaErrorLaunchOutOfResources) {
+    // the grid cannot be made co-resident on this device right now (fewer free SMs than the properties say: a partitioned
+    // or shared GPU): nothing was launched -- the two-kernel path takes the call
+    cudaGetLastError();
+    return SG_OK;
+  }
+  SG_CUDA((cudaError_t)rc);
+  e->last_kernel = name;
   if (x.mode != 0) SG_CUDA(cudaMemcpyAsync(state, x.state_out, state_bytes, cudaMemcpyDeviceToDevice, st));
   e->launches++;
   *done = true;
